@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched C2C FFT hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2fft|reference] [--workload cfg2]
+
+Metric (BASELINE.json): C2C FFT GFLOP/s = 5*N*log2(N)*batch / t, N = x*y*z (reference
+test/test_performance.py:24), plus the achieved fraction of the HBM roofline.  A "step" is one
+out-of-place forward execute of the whole batch (the reference times out-of-place executes,
+test/test_performance.py:26-30).  Default workload = BASELINE.json configs[1]:
+batched 1D complex64 N=4096 batch=65536, normalize=True.
+
+One JSON line on stdout (rank 0).  Multi-GPU (torchrun, one rank per GPU): every rank transforms
+its own full-size batch (weak scaling, no data-path collective), time = max over ranks.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "C2C FFT GFLOP/s (5N log2N)"
+
+# name -> (numpy-order shape, batch, dtype, layout, passes P, description)
+WORKLOADS = {
+    "cfg1": ((1024,), 16, "complex64", 1, "1D complex64 N=1024 batch=16 interleaved"),
+    "cfg2": ((4096,), 65536, "complex64", 1, "1D complex64 N=4096 batch=65536 interleaved normalize=True"),
+    "cfg2s": ((4096,), 65536, "float32", 1, "1D split float32 re/im N=4096 batch=65536 normalize=True"),
+    "cfg3": ((1024, 1024), 256, "complex64", 2, "2D complex64 1024x1024 batch=256"),
+    "cfg4": ((256, 256, 256), 1, "complex128", 3, "3D complex128 256^3 fast_math off"),
+}
+
+
+def flops(shape, batch):
+    n = int(np.prod(shape))
+    return 5.0 * n * math.log2(n) * batch
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock + throttle reasons while the timed region runs."""
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            try:
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+
+    def run(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arms
+def cpu_port_rate(shape, dtype, target_seconds=6.0, max_batch=65536):
+    """Times oracle/pyfft_port.c (the restated reference algorithm, all host threads) on a bounded
+    batch of the same transform; returns (GFLOP/s, threads, sample description, seconds)."""
+    from oracle import numpy_oracle as no
+    from oracle import pyfft_port as pp
+    threads = pp.max_threads()
+    size = int(np.prod(shape))
+    b = max(threads * 4, 64)
+    b = min(b, max_batch)
+    x = no.make_input(shape, b, dtype, seed=1)
+    if isinstance(x, tuple):
+        x = (x[0] + 1j * x[1]).astype(np.complex64 if x[0].dtype == np.float32 else np.complex128)
+    pp.execute(x, shape, b)                                   # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    pp.execute(x, shape, b)
+    dt = time.perf_counter() - t0
+    b2 = int(min(max_batch, max(b, b * target_seconds / max(dt, 1e-6))))
+    if b2 > b * 2:
+        reps = b2 // b
+        x = np.tile(x, (reps,) + (1,) * (x.ndim - 1))
+        b = b * reps
+        t0 = time.perf_counter()
+        pp.execute(x, shape, b)
+        dt = time.perf_counter() - t0
+    rate = flops(shape, b) / dt / 1e9
+    return rate, threads, "batch=%d of shape %s (%d elements), %.2f s wall on %d threads" % (
+        b, "x".join(map(str, shape)), size * b, dt, threads), dt
+
+
+def numpy_scipy_rates(shape, dtype, batch=256):
+    """Informational: pocketfft via numpy (1 thread) and scipy (all workers) on a small sample."""
+    from oracle import numpy_oracle as no
+    out = {}
+    x = no.make_input(shape, batch, dtype, seed=2)
+    if isinstance(x, tuple):
+        x = x[0] + 1j * x[1]
+    axes = tuple(range(1, x.ndim))
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        np.fft.fftn(x, axes=axes)
+        best = min(best, time.perf_counter() - t0)
+    out["numpy_fft_1thread_gflops"] = round(flops(shape, batch) / best / 1e9, 2)
+    try:
+        import scipy.fft as sf
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sf.fftn(x, axes=axes, workers=os.cpu_count())
+            best = min(best, time.perf_counter() - t0)
+        out["scipy_fft_allcores_gflops"] = round(flops(shape, batch) / best / 1e9, 2)
+    except Exception:
+        pass
+    out["sample_batch"] = batch
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle/pyfft_port.c; the real
+    pyfft needs Python 2 + Mako + PyCUDA/PyOpenCL and cannot run in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape, batch, dtype, passes, desc = WORKLOADS[args.workload]
+    from oracle import pyfft_port as pp
+    threads = pp.max_threads()
+    # bounded sample per step: sized from a calibration run so one step is ~1.5 s
+    from oracle import numpy_oracle as no
+    cdt = np.complex64 if np.dtype(dtype) in (np.dtype(np.complex64), np.dtype(np.float32)) else np.complex128
+    b = min(batch, max(threads * 4, 64))
+    x = no.make_input(shape, b, cdt, seed=1)
+    pp.execute(x, shape, b)
+    t0 = time.perf_counter()
+    pp.execute(x, shape, b)
+    dt = time.perf_counter() - t0
+    reps = int(max(1, min(batch // b, 1.5 / max(dt, 1e-6))))
+    if reps > 1:
+        x = np.tile(x, (reps,) + (1,) * (x.ndim - 1))
+        b *= reps
+    out = np.empty_like(x)
+    for _ in range(args.warmup):
+        pp.execute(x, shape, b, out=out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pp.execute(x, shape, b, out=out)
+    el = time.perf_counter() - t0
+    rate = flops(shape, b) * args.steps / el / 1e9
+    sample = "each step = batch %d of %s (of the workload's %d), pyfft algorithm restated in C, OpenMP over lines" % (
+        b, "x".join(map(str, shape)), batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if cdt == np.complex64 else "f64",
+        "data": "synthetic", "config": {"workload": args.workload + ": " + desc, "device": "host CPU"},
+        "cpu_baseline": {"value": round(rate, 3), "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(rate, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_b2fft(args):
+    import torch
+    import torch.distributed as dist
+    from pyfft_b200.cuda import Plan
+    from pyfft_b200.host import HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU (the CUDA path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    shape, batch, dtype, passes, desc = WORKLOADS[args.workload]
+    npdt = np.dtype(dtype)
+    split = npdt.kind == "f"
+    size = int(np.prod(shape))
+    tdt = {"complex64": torch.complex64, "complex128": torch.complex128, "float32": torch.float32,
+           "float64": torch.float64}[dtype]
+    csize = {"complex64": 8, "float32": 8, "complex128": 16, "float64": 16}[dtype]   # bytes per complex element
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+
+    def randn(n):
+        if split:
+            return torch.randn(n, dtype=tdt, device=dev, generator=g)
+        fl = torch.float32 if tdt == torch.complex64 else torch.float64
+        return torch.view_as_complex(torch.randn(n, 2, dtype=fl, device=dev, generator=g))
+
+    n_el = size * batch
+    fast_math = args.workload != "cfg4"
+    plan = Plan(shape, dtype=npdt, normalize=True, fast_math=fast_math, stream=torch.cuda.current_stream(dev),
+                wait_for_finish=False)
+    if split:
+        a_re, a_im, b_re, b_im = randn(n_el), randn(n_el), torch.empty(n_el, dtype=tdt, device=dev), torch.empty(
+            n_el, dtype=tdt, device=dev)
+
+        def step():
+            plan.execute(a_re, a_im, b_re, b_im, batch=batch)
+    else:
+        a, b = randn(n_el), torch.empty(n_el, dtype=tdt, device=dev)
+
+        def step():
+            plan.execute(a, b, batch=batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = plan.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = plan.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = flops(shape, batch) * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel: algorithmic bytes per launch / average launch time
+    peak, peak_src = measured_peaks()
+    compulsory = 2.0 * csize * n_el                         # read every input once + write every output once
+    alg_bytes_per_launch = compulsory                        # every pass is one full read + write of the data
+    per_launch_ms = ms_per_step / passes                     # passes launches per step, equal bytes each
+    achieved = alg_bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
+                "launches_per_step": passes,
+                "compulsory_fraction": round(compulsory / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- end to end: pinned host buffers, H2D + execute + D2H inside the timed region
+    e2e = None
+    if not split and not args.no_e2e:
+        try:
+            e2e_batch = batch
+            pipe = HostPipeline(shape, dtype=npdt, batch=e2e_batch, chunks=args.e2e_chunks, slots=3, device=local_rank,
+                                normalize=True, fast_math=fast_math)
+            h_in = torch.empty(n_el, dtype=tdt).pin_memory()
+            h_out = torch.empty(n_el, dtype=tdt).pin_memory()
+            h_in.copy_(a)
+            for _ in range(2):
+                pipe.run(h_in, h_out)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps_e = max(3, min(args.steps, args.e2e_steps))
+            l0 = pipe.launch_count
+            barrier()
+            e0.record()
+            for _ in range(steps_e):
+                pipe.run(h_in, h_out)
+            e1.record()
+            barrier()
+            e_ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e_ms = float(t.item())
+            e_val = flops(shape, e2e_batch) * world / (e_ms / steps_e * 1e-3) / 1e9
+            e2e = {"value": round(e_val, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(pipe.h2d_bytes),
+                   "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": round(e_ms / steps_e, 3),
+                   "steps": steps_e, "chunks": pipe.chunks, "gpu_launches": pipe.launch_count - l0,
+                   "pcie_gbs_each_way": round(pipe.h2d_bytes / (e_ms / steps_e * 1e-3) / 1e9, 2)}
+            # the result read back equals the device-resident result (same kernels, same data)
+            if rank == 0:
+                chk = torch.empty(size * 4, dtype=tdt, device=dev)
+                Plan(shape, dtype=npdt, normalize=True, fast_math=fast_math).execute(a[:size * 4], chk, batch=4)
+                if not torch.equal(chk.cpu(), h_out[:size * 4]):
+                    e2e["warning"] = "host result differs from device result"
+            del h_in, h_out, pipe
+        except Exception as exc:   # keep the device-resident number even if pinned allocation fails
+            e2e = {"value": None, "unit": "GFLOP/s", "error": str(exc)[:200]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cdt = np.complex64 if csize == 8 else np.complex128
+            rate, threads, sample, _ = cpu_port_rate(shape, cdt, target_seconds=args.cpu_seconds)
+            cpu_baseline = {"value": round(rate, 3), "unit": "GFLOP/s", "cores": threads, "kind": "port",
+                            "sample": sample}
+            cpu_baseline.update(numpy_scipy_rates(shape, cdt, batch=max(1, min(256, (1 << 22) // size))))
+            cpu_baseline["host_cores"] = os.cpu_count()
+        except Exception as exc:
+            cpu_baseline = {"value": None, "error": str(exc)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if csize == 8 else "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "per_gpu_batch": batch, "out_of_place": True,
+                       "l2": "inputs+outputs (%.0f MiB) exceed the 126 MB L2; no flush needed" % (2 * csize * n_el / 2 ** 20)
+                       if 2 * csize * n_el > 2 * 126e6 else "working set fits L2 (launch-bound config)",
+                       "plan": plan.passes, "parallelism": "batch sharded over %d GPU(s), no collective" % world},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b2fft", choices=["b2fft", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=16)
+    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b2fft(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+/* b2fft -- C ABI of the B200-native batched C2C FFT library (libb2fft.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (fjarri-attic/pyfft 0.3.9) has no FFI of its own: its boundary is the Python
+ * operator API  pyfft.cuda.Plan(...) / plan.execute(...)  (pyfft/cuda.py:116-138,
+ * pyfft/plan.py:70-109,173-284).  Each entry point below replaces one piece of that
+ * path; pyfft_b200/plan.py binds them with ctypes and re-creates the Python API on top.
+ *
+ * Conventions: plain C, no torch / CUDA types in the signatures (streams and device
+ * pointers travel as void*), 0 = success, negative = error (see B2FFT_E_*), message in
+ * b2fft_last_error() (thread local).  b2fft_execute never allocates and never
+ * synchronises: all kernels are enqueued on the given stream.
+ */
+#ifndef B2FFT_H_
+#define B2FFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B2FFT_API __attribute__((visibility("default")))
+#else
+#define B2FFT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2FFT_OK 0
+#define B2FFT_E_INVALID (-1)     /* bad argument: Python raises ValueError (pyfft/plan.py:24,48,87-89) */
+#define B2FFT_E_CUDA (-2)        /* CUDA runtime error: RuntimeError */
+#define B2FFT_E_UNSUPPORTED (-3) /* valid request this build has no kernel for: NotImplementedError */
+
+#define B2FFT_F32 0
+#define B2FFT_F64 1
+#define B2FFT_INTERLEAVED 0 /* complex64 / complex128 arrays   (pyfft/plan.py:26-38, split = False) */
+#define B2FFT_SPLIT 1       /* separate re / im real arrays    (pyfft/plan.py:26-38, split = True)  */
+
+#define B2FFT_AXIS_X 1 /* contiguous (last numpy) axis */
+#define B2FFT_AXIS_Y 2
+#define B2FFT_AXIS_Z 4
+
+typedef struct b2fft_plan b2fft_plan;
+
+/* Library version, major*10000 + minor*100 + patch. */
+B2FFT_API int b2fft_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+B2FFT_API const char* b2fft_last_error(void);
+
+/* Replaces FFTPlan.__init__ + _FFTParams + _generateKernelCode (pyfft/plan.py:16-133) and
+ * the Mako render / nvcc compile behind them (pyfft/kernel.py:46-83): validates the shape
+ * (every dimension a power of two, plan.py:23-24), picks the pass list (one DRAM round trip
+ * per axis instead of plan.py:135-171's local/global chains) and uploads twiddle tables.
+ *   dims_xyz   {x, y, z} with x the contiguous axis; unused axes = 1 (plan.py:73-89)
+ *   rank       1, 2 or 3 (informational; axes of length 1 are no-ops)
+ *   precision  B2FFT_F32 | B2FFT_F64,   layout  B2FFT_INTERLEAVED | B2FFT_SPLIT
+ *   normalize, scale   semantics of _FFTKernel.getScaleCoeffFunc (pyfft/kernel.py:23-37):
+ *                      forward *= scale (never normalised); inverse /= scale * (x*y*z if normalize)
+ *   fast_math  1: scaling multiplies by a precomputed reciprocal; 0: true division as the
+ *              reference's stores do (pyfft/kernel.mako:65,271-278).  Twiddles always come from
+ *              tables of correctly rounded values in either mode.
+ *   device     CUDA device ordinal the plan lives on. */
+B2FFT_API int b2fft_plan_create(b2fft_plan** out, int rank, const int64_t dims_xyz[3], int precision, int layout,
+                      int normalize, double scale, int fast_math, int device);
+
+/* Same, but transforms only the axes in axes_mask (B2FFT_AXIS_* bits) and takes the
+ * normalisation size explicitly (norm_size <= 0 means x*y*z); apply_scale = 0 skips the
+ * scale/normalise step.  Used by the slab-decomposed multi-GPU 3D transform, where the
+ * local X/Y passes and the Z pass after the all-to-all are separate plans (no reference
+ * counterpart: the reference is single-device). */
+B2FFT_API int b2fft_plan_create_ex(b2fft_plan** out, const int64_t dims_xyz[3], int axes_mask, int precision, int layout,
+                         int normalize, double scale, int fast_math, int device, double norm_size,
+                         int apply_scale);
+
+/* Replaces the temp-buffer sizing of FFTPlan._execute (pyfft/plan.py:184-192).  The caller
+ * (Python: torch caching allocator or the user's mempool) owns the workspace. */
+B2FFT_API int b2fft_plan_workspace_bytes(const b2fft_plan* plan, int64_t batch, size_t* out);
+B2FFT_API int b2fft_plan_set_workspace(b2fft_plan* plan, void* dptr, size_t bytes);
+
+/* Replaces FFTPlan._execute + Function.__call__ (pyfft/plan.py:173-259, pyfft/cuda.py:35-46).
+ *   interleaved: in0/out0 = complex arrays, in1/out1 = NULL
+ *   split:       in0/in1 = re/im planes, out0/out1 = re/im planes
+ *   out == in means in-place (plan.py:264-266,276-279); otherwise the input is left intact.
+ *   batch transforms are stored back to back (doc/source/index.rst:254-255).
+ *   cuda_stream is a cudaStream_t (NULL = legacy default stream).  Asynchronous. */
+B2FFT_API int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0, void* out1, int inverse,
+                  int64_t batch, void* cuda_stream);
+
+B2FFT_API int b2fft_plan_destroy(b2fft_plan* plan);
+
+/* Replaces Context.wait (pyfft/cuda.py:98-101): blocks until the stream has drained.  Only
+ * needed by callers that hold a raw cudaStream_t; torch callers synchronise their own stream. */
+B2FFT_API int b2fft_stream_synchronize(void* cuda_stream);
+
+/* ---- introspection (used by bench.py / tests) ---- */
+B2FFT_API int b2fft_plan_num_passes(const b2fft_plan* plan);
+/* One line per pass: "axis=X n=4096 inner=1 variant=float_n12_w1_..." */
+B2FFT_API int b2fft_plan_describe(const b2fft_plan* plan, char* buf, size_t buflen);
+/* Number of kernels this plan has launched since creation (bench.py's gpu_launches). */
+B2FFT_API int64_t b2fft_plan_launch_count(const b2fft_plan* plan);
+
+/* ---- kernel-variant tuning interface ---- */
+B2FFT_API int b2fft_num_variants(void);
+/* "name prec log2n W G E S threads smem_bytes minb occupancy" */
+B2FFT_API int b2fft_variant_info(int index, char* buf, size_t buflen);
+/* Runs ONE pass of variant `index` over n_tiles tiles of an [outer][N][inner] array. */
+B2FFT_API int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, void* out1, int split,
+                      int inverse, int64_t n_tiles, int64_t inner, int device, void* cuda_stream);
+/* Comma-separated variant names that take precedence over the default preference order when
+ * plans are created afterwards ("" clears).  Also read from $B2FFT_PREFER at load time. */
+B2FFT_API int b2fft_set_preferred_variants(const char* names);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2FFT_H_ */

@@ -1,0 +1,412 @@
+// C ABI of libb2fft.so: plan objects, the host planner and the launch loop.
+// See include/b2fft.h for the contract and the reference lines each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/b2fft.h"
+#include "kernels.cuh"
+#include "twiddle.h"
+
+namespace {
+
+using b2::KernelVariant;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail(B2FFT_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));     \
+    } while (0)
+
+// ------------------------------------------------------------------ registry
+struct Registry {
+    std::vector<KernelVariant> v;
+    std::vector<bool> prepared;
+    std::vector<std::string> preferred;
+    std::mutex mu;
+    Registry() {
+        b2::register_f32_row(v);
+        b2::register_f32_col(v);
+        b2::register_f64_row(v);
+        b2::register_f64_col(v);
+        prepared.assign(v.size(), false);
+        if (const char* e = getenv("B2FFT_PREFER")) set_preferred(e);
+    }
+    void set_preferred(const char* names) {
+        preferred.clear();
+        std::stringstream ss(names ? names : "");
+        std::string tok;
+        while (std::getline(ss, tok, ',')) {
+            size_t a = tok.find_first_not_of(" \t"), b = tok.find_last_not_of(" \t");
+            if (a != std::string::npos) preferred.push_back(tok.substr(a, b - a + 1));
+        }
+    }
+    // contiguous axis -> W == 1; strided axis -> largest-preference W dividing `inner`
+    int pick(int prec, int log2n, bool contiguous, long long inner) {
+        auto ok = [&](const KernelVariant& k) {
+            if (k.prec != prec || k.log2n != log2n) return false;
+            if (contiguous) return k.W == 1;
+            return k.W > 1 ? (inner % k.W == 0) : false;
+        };
+        for (const auto& name : preferred)
+            for (size_t i = 0; i < v.size(); ++i)
+                if (name == v[i].name && ok(v[i])) return (int)i;
+        for (size_t i = 0; i < v.size(); ++i)
+            if (ok(v[i])) return (int)i;
+        if (!contiguous)   // narrow inner dimension: fall back to one column per tile (strided, uncoalesced)
+            for (size_t i = 0; i < v.size(); ++i)
+                if (v[i].prec == prec && v[i].log2n == log2n && v[i].W == 1) return (int)i;
+        return -1;
+    }
+    cudaError_t prepare(int idx) {
+        std::lock_guard<std::mutex> lk(mu);
+        // function attributes are per device context; cheap enough to redo per plan
+        return v[idx].prepare();
+    }
+};
+Registry& registry() {
+    static Registry r;
+    return r;
+}
+
+// ------------------------------------------------------------------ twiddle cache
+struct TwiddleCache {
+    std::mutex mu;
+    std::map<std::tuple<int, int, int, int>, void*> tabs;   // (device, prec, NS, R) -> device pointer
+    int get(int device, int prec, int NS, int R, const void** out) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_tuple(device, prec, NS, R);
+        auto it = tabs.find(key);
+        if (it != tabs.end()) { *out = it->second; return 0; }
+        void* d = nullptr;
+        size_t bytes;
+        if (prec == B2FFT_F32) {
+            auto h = b2::make_stage_table<float>(NS, R);
+            bytes = h.size() * sizeof(h[0]);
+            CUDA_TRY(cudaMalloc(&d, bytes));
+            CUDA_TRY(cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice));
+        } else {
+            auto h = b2::make_stage_table<double>(NS, R);
+            bytes = h.size() * sizeof(h[0]);
+            CUDA_TRY(cudaMalloc(&d, bytes));
+            CUDA_TRY(cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice));
+        }
+        tabs[key] = d;
+        *out = d;
+        return 0;
+    }
+};
+TwiddleCache& twiddles() {
+    static TwiddleCache c;
+    return c;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            changed = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2ll(long long v) {
+    int l = 0;
+    while ((1LL << l) < v) ++l;
+    return l;
+}
+
+struct Pass {
+    int variant;
+    int axis;              // 0 = x, 1 = y, 2 = z
+    int log2n;
+    long long n;
+    long long inner;       // element stride of the transformed axis
+    long long outer;       // lines groups per transform: number of [n][inner] blocks per single transform
+    const void* tw[3];
+};
+
+}  // namespace
+
+struct b2fft_plan {
+    long long x, y, z;
+    int axes_mask;
+    int prec, layout, normalize, fast_math, device;
+    double scale, norm_size;
+    int apply_scale;
+    std::vector<Pass> passes;
+    void* workspace = nullptr;
+    size_t workspace_bytes = 0;
+    std::atomic<long long> launches{0};
+};
+
+namespace {
+
+int build_passes(b2fft_plan* pl) {
+    Registry& reg = registry();
+    const long long dims[3] = {pl->x, pl->y, pl->z};
+    const long long inner[3] = {1, pl->x, pl->x * pl->y};
+    const long long outer[3] = {pl->y * pl->z, pl->z, 1};
+    for (int a = 0; a < 3; ++a) {
+        if (!(pl->axes_mask & (1 << a)) || dims[a] <= 1) continue;
+        const int lg = ilog2ll(dims[a]);
+        int vi = reg.pick(pl->prec, lg, a == 0, inner[a]);
+        if (vi < 0)
+            return fail(B2FFT_E_UNSUPPORTED, "no kernel for axis %c of length %lld (%s) in this build", "xyz"[a],
+                        dims[a], pl->prec ? "f64" : "f32");
+        const KernelVariant& kv = reg.v[vi];
+        Pass p{};
+        p.variant = vi;
+        p.axis = a;
+        p.log2n = lg;
+        p.n = dims[a];
+        p.inner = inner[a];
+        p.outer = outer[a];
+        int NS = (int)dims[a];
+        for (int s = 0; s + 1 < kv.S; ++s) {
+            int rc = twiddles().get(pl->device, pl->prec, NS, kv.radix[s], &p.tw[s]);
+            if (rc) return rc;
+            NS /= kv.radix[s];
+        }
+        cudaError_t e = reg.prepare(vi);
+        if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+        pl->passes.push_back(p);
+    }
+    return 0;
+}
+
+template <typename T>
+int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1, void* out0, void* out1, int inverse,
+                long long batch, bool last, cudaStream_t stream) {
+    const KernelVariant& kv = registry().v[ps.variant];
+    b2::PassParams<T> p{};
+    const bool split = pl->layout == B2FFT_SPLIT;
+    if (split && inverse) {   // IDFT(z) = swap(DFT(swap(z))): swap the planes instead of the registers
+        p.in0 = (const T*)in1; p.in1 = (const T*)in0; p.out0 = (T*)out1; p.out1 = (T*)out0;
+    } else {
+        p.in0 = (const T*)in0; p.in1 = (const T*)in1; p.out0 = (T*)out0; p.out1 = (T*)out1;
+    }
+    for (int s = 0; s < 3; ++s) p.tw[s] = (const T*)ps.tw[s];
+    p.inner = ps.inner;
+    p.inner_blocks = ps.inner / kv.W;
+    p.outer_stride = ps.n * ps.inner;
+    p.n_tiles = batch * ps.outer * p.inner_blocks;
+    p.scale = (T)1;
+    p.scale_mode = 0;
+    if (last && pl->apply_scale) {
+        // pyfft/kernel.py:23-37: forward divides by 1/scale, inverse by scale * (size if normalize)
+        double coeff = inverse ? (pl->normalize ? pl->norm_size : 1.0) * pl->scale : 1.0 / pl->scale;
+        if (coeff != 1.0) {
+            if (pl->fast_math) { p.scale = (T)(1.0 / coeff); p.scale_mode = 1; }
+            else { p.scale = (T)coeff; p.scale_mode = 2; }
+        }
+    }
+    cudaError_t e = kv.launch(split ? 1 : 0, inverse ? 1 : 0, &p, stream);
+    if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "launch of %s failed: %s", kv.name, cudaGetErrorString(e));
+    pl->launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2fft_version(void) { return 100; }
+
+const char* b2fft_last_error(void) { return g_err.c_str(); }
+
+int b2fft_plan_create_ex(b2fft_plan** out, const int64_t dims_xyz[3], int axes_mask, int precision, int layout,
+                         int normalize, double scale, int fast_math, int device, double norm_size, int apply_scale) {
+    if (!out || !dims_xyz) return fail(B2FFT_E_INVALID, "null argument");
+    *out = nullptr;
+    for (int a = 0; a < 3; ++a)
+        if (!is_pow2(dims_xyz[a])) return fail(B2FFT_E_INVALID, "Array dimensions must be powers of two");
+    if (precision != B2FFT_F32 && precision != B2FFT_F64) return fail(B2FFT_E_INVALID, "bad precision %d", precision);
+    if (layout != B2FFT_INTERLEAVED && layout != B2FFT_SPLIT) return fail(B2FFT_E_INVALID, "bad layout %d", layout);
+    if (!(scale == scale) || scale == 0.0) return fail(B2FFT_E_INVALID, "scale must be a non-zero number");
+    if (axes_mask < 0 || axes_mask > 7) return fail(B2FFT_E_INVALID, "bad axes mask %d", axes_mask);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(B2FFT_E_INVALID, "bad device %d (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(B2FFT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+
+    b2fft_plan* pl = new b2fft_plan();
+    pl->x = dims_xyz[0]; pl->y = dims_xyz[1]; pl->z = dims_xyz[2];
+    pl->axes_mask = axes_mask;
+    pl->prec = precision; pl->layout = layout; pl->normalize = normalize ? 1 : 0; pl->fast_math = fast_math ? 1 : 0;
+    pl->device = device;
+    pl->scale = scale;
+    pl->norm_size = norm_size > 0 ? norm_size : (double)pl->x * (double)pl->y * (double)pl->z;
+    pl->apply_scale = apply_scale ? 1 : 0;
+    int rc = build_passes(pl);
+    if (rc) { delete pl; return rc; }
+    *out = pl;
+    return B2FFT_OK;
+}
+
+int b2fft_plan_create(b2fft_plan** out, int rank, const int64_t dims_xyz[3], int precision, int layout, int normalize,
+                      double scale, int fast_math, int device) {
+    if (rank < 1 || rank > 3) return fail(B2FFT_E_INVALID, "Wrong shape");
+    return b2fft_plan_create_ex(out, dims_xyz, B2FFT_AXIS_X | B2FFT_AXIS_Y | B2FFT_AXIS_Z, precision, layout, normalize,
+                                scale, fast_math, device, 0.0, 1);
+}
+
+int b2fft_plan_workspace_bytes(const b2fft_plan* plan, int64_t batch, size_t* out) {
+    if (!plan || !out || batch < 0) return fail(B2FFT_E_INVALID, "bad argument");
+    *out = 0;   // every pass works tile-in-place; no pass needs scratch memory
+    return B2FFT_OK;
+}
+
+int b2fft_plan_set_workspace(b2fft_plan* plan, void* dptr, size_t bytes) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    plan->workspace = dptr;
+    plan->workspace_bytes = bytes;
+    return B2FFT_OK;
+}
+
+int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0, void* out1, int inverse,
+                  int64_t batch, void* cuda_stream) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (batch < 0) return fail(B2FFT_E_INVALID, "negative batch");
+    const bool split = plan->layout == B2FFT_SPLIT;
+    if (!in0 || !out0 || (split && (!in1 || !out1))) return fail(B2FFT_E_INVALID, "null data pointer");
+    const size_t align = split ? (plan->prec ? 8 : 4) : (plan->prec ? 16 : 8);
+    const void* ptrs[4] = {in0, in1, out0, out1};
+    for (int i = 0; i < 4; ++i)
+        if (ptrs[i] && ((uintptr_t)ptrs[i] % align) != 0)
+            return fail(B2FFT_E_INVALID, "device pointer %d is not %zu-byte aligned", i, align);
+    if (batch == 0) return B2FFT_OK;
+    DeviceGuard guard(plan->device);
+    if (guard.err != cudaSuccess) return fail(B2FFT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    if (plan->passes.empty()) {   // all axes of length 1 (or masked out): identity (times the scale), as a copy
+        if (in0 != out0 || (split && in1 != out1)) {
+            const size_t esz = (plan->prec ? 8 : 4) * (split ? 1 : 2);
+            const size_t bytes = (size_t)(plan->x * plan->y * plan->z) * (size_t)batch * esz;
+            CUDA_TRY(cudaMemcpyAsync(out0, in0, bytes, cudaMemcpyDeviceToDevice, stream));
+            if (split) CUDA_TRY(cudaMemcpyAsync(out1, in1, bytes, cudaMemcpyDeviceToDevice, stream));
+        }
+        return B2FFT_OK;
+    }
+    const void* ci0 = in0;
+    const void* ci1 = in1;
+    for (size_t i = 0; i < plan->passes.size(); ++i) {
+        const bool last = i + 1 == plan->passes.size();
+        int rc = plan->prec == B2FFT_F32
+                     ? launch_pass<float>(plan, plan->passes[i], ci0, ci1, out0, out1, inverse, batch, last, stream)
+                     : launch_pass<double>(plan, plan->passes[i], ci0, ci1, out0, out1, inverse, batch, last, stream);
+        if (rc) return rc;
+        ci0 = out0;   // later passes run in place on the output
+        ci1 = out1;
+    }
+    return B2FFT_OK;
+}
+
+int b2fft_plan_destroy(b2fft_plan* plan) {
+    delete plan;
+    return B2FFT_OK;
+}
+
+int b2fft_stream_synchronize(void* cuda_stream) {
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    return B2FFT_OK;
+}
+
+int b2fft_plan_num_passes(const b2fft_plan* plan) { return plan ? (int)plan->passes.size() : B2FFT_E_INVALID; }
+
+int b2fft_plan_describe(const b2fft_plan* plan, char* buf, size_t buflen) {
+    if (!plan || !buf || !buflen) return fail(B2FFT_E_INVALID, "bad argument");
+    std::string s;
+    for (const Pass& p : plan->passes) {
+        char line[256];
+        snprintf(line, sizeof line, "axis=%c n=%lld inner=%lld variant=%s\n", "XYZ"[p.axis], p.n, p.inner,
+                 registry().v[p.variant].name);
+        s += line;
+    }
+    snprintf(buf, buflen, "%s", s.c_str());
+    return B2FFT_OK;
+}
+
+int64_t b2fft_plan_launch_count(const b2fft_plan* plan) { return plan ? (int64_t)plan->launches.load() : -1; }
+
+int b2fft_num_variants(void) { return (int)registry().v.size(); }
+
+int b2fft_variant_info(int index, char* buf, size_t buflen) {
+    Registry& reg = registry();
+    if (index < 0 || index >= (int)reg.v.size() || !buf || !buflen) return fail(B2FFT_E_INVALID, "bad argument");
+    const KernelVariant& k = reg.v[index];
+    int occ = -1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && reg.prepare(index) == cudaSuccess) occ = k.occupancy();
+    else cudaGetLastError();
+    snprintf(buf, buflen, "%s %d %d %d %d %d %d %d %lld %d %d", k.name, k.prec, k.log2n, k.W, k.G, k.E, k.S, k.threads,
+             k.smem_bytes, k.minb, occ);
+    return B2FFT_OK;
+}
+
+int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, void* out1, int split, int inverse,
+                      int64_t n_tiles, int64_t inner, int device, void* cuda_stream) {
+    Registry& reg = registry();
+    if (index < 0 || index >= (int)reg.v.size()) return fail(B2FFT_E_INVALID, "bad variant index");
+    const KernelVariant& k = reg.v[index];
+    if (inner % k.W != 0) return fail(B2FFT_E_INVALID, "inner %lld not a multiple of W=%d", (long long)inner, k.W);
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(B2FFT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    b2fft_plan tmp;   // only used for bookkeeping of launch_pass
+    tmp.prec = k.prec; tmp.layout = split ? B2FFT_SPLIT : B2FFT_INTERLEAVED; tmp.apply_scale = 0; tmp.device = device;
+    Pass p{};
+    p.variant = index; p.log2n = k.log2n; p.n = 1LL << k.log2n; p.inner = inner;
+    int NS = (int)p.n;
+    for (int s = 0; s + 1 < k.S; ++s) {
+        int rc = twiddles().get(device, k.prec, NS, k.radix[s], &p.tw[s]);
+        if (rc) return rc;
+        NS /= k.radix[s];
+    }
+    cudaError_t e = reg.prepare(index);
+    if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+    // launch_pass computes n_tiles = batch * outer * inner_blocks; fold everything into `outer`
+    const long long inner_blocks = inner / k.W;
+    if (n_tiles % inner_blocks != 0) return fail(B2FFT_E_INVALID, "n_tiles must be a multiple of inner/W");
+    p.outer = n_tiles / inner_blocks;
+    return k.prec == B2FFT_F32
+               ? launch_pass<float>(&tmp, p, in0, in1, out0, out1, inverse, 1, false, (cudaStream_t)cuda_stream)
+               : launch_pass<double>(&tmp, p, in0, in1, out0, out1, inverse, 1, false, (cudaStream_t)cuda_stream);
+}
+
+int b2fft_set_preferred_variants(const char* names) {
+    registry().set_preferred(names);
+    return B2FFT_OK;
+}
+
+}  // extern "C"

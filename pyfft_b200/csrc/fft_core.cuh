@@ -1,0 +1,351 @@
+// b2fft core: in-register radix butterflies and the "tile FFT" thread program.
+//
+// One CTA processes G tiles.  A tile is W adjacent columns of an [outer][N][inner]
+// array (FFT along N, element stride `inner`); W = 1, inner = 1 is the contiguous
+// (row / X-axis) case, W > 1 the strided-axis (Y / Z) case where the W columns are
+// W consecutive elements of the contiguous dimension, so every global access of a
+// warp covers whole 128-byte lines.  Each thread owns E = R0 elements of one
+// column for the whole transform: data goes HBM -> registers once, through S
+// Stockham/DIF stages with S-1 shared-memory exchanges, and registers -> HBM once.
+// This replaces the reference's localKernel (pyfft/kernel.mako:725-803) and
+// globalKernel (805-1047); the mathematics per stage is the same DIF step
+//     n_rem = m + M*j  --radix-R butterfly over j, times w_{N_s}^{m k}-->  (K + P*k, m)
+// with natural-order output, but twiddles come from precomputed tables instead of
+// on-the-fly sincos (kernel.mako:35-44,566-597).
+//
+// Everything here is __host__ __device__ so tests/host_emu can run the exact same
+// thread program on the CPU, phase by phase (test infrastructure; the product only
+// ever launches the __global__ wrappers in kernels.cuh).
+#pragma once
+
+#include <stdint.h>
+#include <type_traits>
+#include <utility>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b2 {
+
+// ------------------------------------------------------------------ small utilities
+template <typename T> struct vec2;
+template <> struct alignas(8) vec2<float> { float x, y; };
+template <> struct alignas(16) vec2<double> { double x, y; };
+
+template <int B, int E_, class F>
+B2_HD void static_for(F&& f) {
+    if constexpr (B < E_) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E_>(static_cast<F&&>(f));
+    }
+}
+
+constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+constexpr int brev(int v, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// cos(2*pi*e/64), e = 0..16 (first quadrant incl. end points), round-to-nearest doubles.
+constexpr double kCosQ64[17] = {
+    1.0,
+    0.99518472667219688624, 0.98078528040323044913, 0.95694033573220886494,
+    0.92387953251128675613, 0.88192126434835502971, 0.83146961230254523708,
+    0.77301045336273696081, 0.70710678118654752440, 0.63439328416364549822,
+    0.55557023301960222474, 0.47139673682599764856, 0.38268343236508977173,
+    0.29028467725446236764, 0.19509032201612826785, 0.09801714032956060199,
+    0.0};
+constexpr double cos64(int e) {  // e in [0, 32]
+    return e <= 16 ? kCosQ64[e] : -kCosQ64[32 - e];
+}
+constexpr double sin64(int e) {  // e in [0, 32]
+    return e <= 16 ? kCosQ64[16 - e] : kCosQ64[e - 16];
+}
+
+// (dr + i di) * exp(-2*pi*i*e/64), e in [0, 32) compile-time.
+template <int e, typename T>
+B2_HD void mul_w64(T dr, T di, T& orr, T& oi) {
+    if constexpr (e == 0) {
+        orr = dr; oi = di;
+    } else if constexpr (e == 16) {
+        orr = di; oi = -dr;
+    } else if constexpr (e == 8) {
+        constexpr T h = (T)0.70710678118654752440;
+        orr = (dr + di) * h; oi = (di - dr) * h;
+    } else if constexpr (e == 24) {
+        constexpr T h = (T)0.70710678118654752440;
+        orr = (di - dr) * h; oi = -(dr + di) * h;
+    } else {
+        constexpr T c = (T)cos64(e);
+        constexpr T s = (T)sin64(e);
+        orr = dr * c + di * s;
+        oi = di * c - dr * s;
+    }
+}
+
+// In-register forward radix-R DIF FFT on re/im[OFF .. OFF+R).  X[k] ends up at
+// register OFF + brev(k, log2 R) (no data movement for the permutation).
+template <int R, int OFF, typename T>
+B2_HD void butterfly(T* re, T* im) {
+    static_assert(R >= 1 && R <= 64 && (R & (R - 1)) == 0, "radix must be a power of two <= 64");
+    constexpr int LG = ilog2(R);
+    static_for<0, LG>([&](auto lc) {
+        constexpr int len = R >> decltype(lc)::value;
+        constexpr int half = len / 2;
+        static_for<0, R / 2>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            constexpr int ia = OFF + (q / half) * len + (q % half);
+            constexpr int ib = ia + half;
+            constexpr int e = (q % half) * (64 / len);
+            T ur = re[ia], ui = im[ia], vr = re[ib], vi = im[ib];
+            re[ia] = ur + vr;
+            im[ia] = ui + vi;
+            mul_w64<e>(ur - vr, ui - vi, re[ib], im[ib]);
+        });
+    });
+}
+
+// ------------------------------------------------------------------ pass parameters
+template <typename T>
+struct PassParams {
+    const T* in0;   // interleaved: vec2<T>* ; split: re plane
+    const T* in1;   // split: im plane (else unused)
+    T* out0;
+    T* out1;
+    const T* tw[3];          // per-exchange-stage twiddle tables (vec2<T>), layout [(k-1)*M + m]
+    long long n_tiles;       // total number of tiles (columns / W)
+    long long inner;         // element stride between consecutive n (1 for the contiguous axis)
+    long long inner_blocks;  // inner / W
+    long long outer_stride;  // N * inner
+    T scale;                 // multiplier (scale_mode 1) or divisor (scale_mode 2)
+    int scale_mode;          // 0: none
+};
+
+// ------------------------------------------------------------------ compile-time plan
+// ESZ_ = bytes per complex element in shared memory (8 or 16), used for the
+// bank-conflict padding rule only.
+template <typename T_, int LOG2N_, int W_, int G_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+struct TileCfg {
+    using T = T_;
+    static constexpr int LOG2N = LOG2N_;
+    static constexpr int N = 1 << LOG2N_;
+    static constexpr int W = W_;
+    static constexpr int G = G_;
+    static constexpr int E = R0_;
+    static constexpr int S = 1 + (R1_ > 1) + (R2_ > 1) + (R3_ > 1);
+    static constexpr int TPC = N / E;            // threads per column
+    static constexpr int THREADS = TPC * W * G;  // threads per CTA
+    static_assert(R0_ * R1_ * R2_ * R3_ == N, "radices must multiply to N");
+    static_assert(R0_ >= R1_ && R0_ >= R2_ && R0_ >= R3_, "R0 must be the largest radix");
+    static_assert(R1_ > 1 || (R2_ == 1 && R3_ == 1), "radices must be packed to the front");
+    static_assert(R2_ > 1 || R3_ == 1, "radices must be packed to the front");
+
+    static constexpr int R(int s) { return s == 0 ? R0_ : s == 1 ? R1_ : s == 2 ? R2_ : R3_; }
+    static constexpr int P(int s) { return s <= 0 ? 1 : P(s - 1) * R(s - 1); }   // radices done before s
+    static constexpr int NS(int s) { return N / P(s); }                         // remaining length
+    static constexpr int M(int s) { return NS(s) / R(s); }
+    static constexpr int BPT(int s) { return E / R(s); }                        // butterflies / thread
+
+    // conflict-free group: consecutive column-threads that share one shared-memory wavefront
+    static constexpr int CF = (sizeof(T) == 4 ? 16 : 8);
+    static constexpr int CFE = (CF / W) < 1 ? 1 : (CF / W);
+    // exchange s sits between stage s and s+1
+    static constexpr int PAD(int s) { return M(s + 1) < CFE ? M(s + 1) : 0; }
+    static constexpr int ROW(int s) { return M(s); }
+    static constexpr int PADN(int s) { return N + (N / ROW(s)) * PAD(s); }
+    static constexpr int max_padn() {
+        int m = 0;
+        for (int s = 0; s + 1 < S; ++s) m = PADN(s) > m ? PADN(s) : m;
+        return m;
+    }
+    static constexpr int COL_SMEM = max_padn();                 // complex elements per column
+    static constexpr long long SMEM_BYTES = (long long)COL_SMEM * W * G * 2 * sizeof(T);
+};
+
+// ------------------------------------------------------------------ global memory access
+template <typename T>
+B2_HD vec2<T> ld_stream(const vec2<T>* p) {
+#if defined(__CUDA_ARCH__)
+    vec2<T> v;
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    } else {
+        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    }
+    return v;
+#else
+    return *p;
+#endif
+}
+template <typename T>
+B2_HD T ld_stream1(const T* p) {
+#if defined(__CUDA_ARCH__)
+    T v;
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    } else {
+        asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    }
+    return v;
+#else
+    return *p;
+#endif
+}
+
+// ------------------------------------------------------------------ the thread program
+template <class Cfg, bool SPLIT, bool INV>
+struct TileThread {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    static constexpr int E = Cfg::E, N = Cfg::N, W = Cfg::W, S = Cfg::S, TPC = Cfg::TPC;
+
+    T re[E], im[E];
+    int t, w, g;          // thread-in-column, column-in-tile, tile-in-CTA
+    bool active;
+    long long base;       // element offset of (n = 0, this column)
+
+    B2_HD void setup(int tid, long long bid, const PassParams<T>& p) {
+        w = tid % W;
+        t = (tid / W) % TPC;
+        g = tid / (W * TPC);
+        long long tile = bid * Cfg::G + g;
+        active = tile < p.n_tiles;
+        long long o = 0, ib = tile;
+        if (p.inner_blocks > 1) { o = tile / p.inner_blocks; ib = tile - o * p.inner_blocks; }
+        else { o = tile; ib = 0; }
+        base = o * p.outer_stride + ib * W + w;
+    }
+
+    // ---- stage 0 input: element n = t + TPC*j  (BPT(0) == 1)
+    B2_HD void load(const PassParams<T>& p) {
+        if (!active) {
+            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] = 0; im[decltype(jc)::value] = 0; });
+            return;
+        }
+        if constexpr (SPLIT) {
+            const T* pr = p.in0 + base + (long long)t * p.inner;
+            const T* pi = p.in1 + base + (long long)t * p.inner;
+            const long long step = (long long)TPC * p.inner;
+            static_for<0, E>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                re[j] = ld_stream1(pr + j * step);
+                im[j] = ld_stream1(pi + j * step);
+            });
+        } else {
+            const T2* pc = reinterpret_cast<const T2*>(p.in0) + base + (long long)t * p.inner;
+            const long long step = (long long)TPC * p.inner;
+            static_for<0, E>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                T2 v = ld_stream(pc + j * step);
+                if constexpr (INV) { re[j] = v.y; im[j] = v.x; }   // IDFT(z) = swap(DFT(swap(z)))
+                else { re[j] = v.x; im[j] = v.y; }
+            });
+        }
+    }
+
+    // ---- butterflies of stage s, then the stage twiddle (not after the last stage)
+    template <int s>
+    B2_HD void compute(const PassParams<T>& p) {
+        constexpr int R = Cfg::R(s);
+        static_for<0, Cfg::BPT(s)>([&](auto ic) { butterfly<R, decltype(ic)::value * R>(re, im); });
+        if constexpr (s + 1 < S) {
+            constexpr int M = Cfg::M(s);
+            constexpr int LG = ilog2(R);
+            const T2* tw = reinterpret_cast<const T2*>(p.tw[s]) + (t % M);
+            static_for<1, R>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const T2 wv = tw[(k - 1) * M];
+                static_for<0, Cfg::BPT(s)>([&](auto ic) {
+                    constexpr int q = decltype(ic)::value * R + brev(k, LG);
+                    const T xr = re[q], xi = im[q];
+                    re[q] = xr * wv.x - xi * wv.y;
+                    im[q] = xr * wv.y + xi * wv.x;
+                });
+            });
+        }
+    }
+
+    // ---- exchange s: write outputs of stage s.  pos = b + k*(N/R), b = t + TPC*i, padded.
+    template <int s>
+    B2_HD void xwrite(T2* smem) const {
+        constexpr int R = Cfg::R(s), LG = ilog2(R), BPT = Cfg::BPT(s);
+        constexpr int ROW = Cfg::ROW(s), PAD = Cfg::PAD(s);
+        static_assert(TPC % ROW == 0, "threads per column must be a multiple of the row length");
+        constexpr int TW = TPC + (TPC / ROW) * PAD;       // padded distance between consecutive (i + k*BPT)
+        T2* dst = smem + ((long long)g * Cfg::COL_SMEM + t + (t / ROW) * PAD) * W + w;
+        static_for<0, BPT>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            static_for<0, R>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr int q = i * R + brev(k, LG);
+                T2 v; v.x = re[q]; v.y = im[q];
+                dst[(i + k * BPT) * TW * W] = v;
+            });
+        });
+    }
+
+    // ---- exchange s: read inputs of stage s+1.  b' = t + TPC*i' -> (K', m'); element j' at
+    //      K'*(M(s)+PAD) + m' + M(s+1)*j'
+    template <int s>
+    B2_HD void xread(const T2* smem) {
+        constexpr int R1 = Cfg::R(s + 1), BPT1 = Cfg::BPT(s + 1);
+        constexpr int M1 = Cfg::M(s + 1);
+        constexpr int ROWP = Cfg::M(s) + Cfg::PAD(s);
+        static_assert(TPC % M1 == 0, "threads per column must be a multiple of M(s+1)");
+        const T2* src = smem + ((long long)g * Cfg::COL_SMEM + (t / M1) * ROWP + (t % M1)) * W + w;
+        static_for<0, BPT1>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            static_for<0, R1>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const T2 v = src[(i * (TPC / M1) * ROWP + j * M1) * W];
+                re[i * R1 + j] = v.x;
+                im[i * R1 + j] = v.y;
+            });
+        });
+    }
+
+    // ---- final output: n = t + TPC*(i + k*BPT) in natural order, scaled
+    B2_HD void store(const PassParams<T>& p) {
+        if (!active) return;
+        constexpr int s = S - 1;
+        constexpr int R = Cfg::R(s), LG = ilog2(R), BPT = Cfg::BPT(s);
+        if (p.scale_mode == 1) {
+            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] *= p.scale; im[decltype(jc)::value] *= p.scale; });
+        } else if (p.scale_mode == 2) {
+            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] /= p.scale; im[decltype(jc)::value] /= p.scale; });
+        }
+        const long long step = (long long)TPC * p.inner;
+        if constexpr (SPLIT) {
+            T* pr = p.out0 + base + (long long)t * p.inner;
+            T* pi = p.out1 + base + (long long)t * p.inner;
+            static_for<0, BPT>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                static_for<0, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int q = i * R + brev(k, LG);
+                    pr[(i + k * BPT) * step] = re[q];
+                    pi[(i + k * BPT) * step] = im[q];
+                });
+            });
+        } else {
+            T2* pc = reinterpret_cast<T2*>(p.out0) + base + (long long)t * p.inner;
+            static_for<0, BPT>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                static_for<0, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int q = i * R + brev(k, LG);
+                    T2 v;
+                    if constexpr (INV) { v.x = im[q]; v.y = re[q]; }
+                    else { v.x = re[q]; v.y = im[q]; }
+                    pc[(i + k * BPT) * step] = v;
+                });
+            });
+        }
+    }
+};
+
+}  // namespace b2

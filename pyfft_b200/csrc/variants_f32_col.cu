@@ -1,0 +1,11 @@
+// Kernel instantiations for group F32_COL (see variants.def).
+#include "kernels.cuh"
+
+namespace b2 {
+void register_f32_col(std::vector<KernelVariant>& out) {
+#define B2_GROUP_F32_COL
+#define X B2_V
+#include "variants.def"
+#undef X
+}
+}  // namespace b2

@@ -1,0 +1,11 @@
+// Kernel instantiations for group F64_ROW (see variants.def).
+#include "kernels.cuh"
+
+namespace b2 {
+void register_f64_row(std::vector<KernelVariant>& out) {
+#define B2_GROUP_F64_ROW
+#define X B2_V
+#include "variants.def"
+#undef X
+}
+}  // namespace b2

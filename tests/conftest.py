@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libb2fft.so, built in-tree if missing (nvcc cross-compiles without a GPU)."""
+    from pyfft_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from pyfft_b200.build import build
+        build()
+    return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible (the CUDA path has no fallback)")
+    return torch.device("cuda:0")
