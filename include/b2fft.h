@@ -112,6 +112,11 @@ B2FFT_API int b2fft_run_variant(int index, const void* in0, const void* in1, voi
  * plans are created afterwards ("" clears).  Also read from $B2FFT_PREFER at load time. */
 B2FFT_API int b2fft_set_preferred_variants(const char* names);
 
+/* Global tuning options.  "l2_chunk_bytes": multi-pass transforms run their passes chunk by
+ * chunk so the intermediate stays in the 126 MB L2 between passes (bytes; default 0 = whole-array
+ * passes, also settable through $B2FFT_L2_CHUNK_MB). */
+B2FFT_API int b2fft_set_option(const char* key, double value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SIGNATURES = {
     "b2fft_variant_info": (_i, [_i, ctypes.c_char_p, _sz]),
     "b2fft_run_variant": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _i, _vp]),
     "b2fft_set_preferred_variants": (_i, [ctypes.c_char_p]),
+    "b2fft_set_option": (_i, [ctypes.c_char_p, _d]),
 }
 
 

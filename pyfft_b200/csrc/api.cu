@@ -24,6 +24,15 @@ using b2::KernelVariant;
 
 thread_local std::string g_err;
 
+// L2-resident multi-pass execution: consecutive passes run chunk by chunk so that the data a
+// pass wrote is still in the 126 MB L2 when the next pass reads it (0 disables).  Measured on
+// B200 (profiles/r01_l2_chunking.md): with one kernel launch per chunk and pass the launch/drain
+// overhead of the many short kernels outweighs the saved DRAM traffic, so the default is off.
+std::atomic<long long> g_l2_chunk_bytes{[] {
+    const char* e = getenv("B2FFT_L2_CHUNK_MB");
+    return (long long)((e ? atof(e) : 0.0) * 1024.0 * 1024.0);
+}()};
+
 int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -50,6 +59,7 @@ struct Registry {
         b2::register_f32_col(v);
         b2::register_f64_row(v);
         b2::register_f64_col(v);
+        b2::register_exp(v);   // tuning candidates, never picked by default (listed last)
         prepared.assign(v.size(), false);
         if (const char* e = getenv("B2FFT_PREFER")) set_preferred(e);
     }
@@ -67,16 +77,20 @@ struct Registry {
         auto ok = [&](const KernelVariant& k) {
             if (k.prec != prec || k.log2n != log2n) return false;
             if (contiguous) return k.W == 1;
-            return k.W > 1 ? (inner % k.W == 0) : false;
+            return (k.W > 1 && k.kind == 0) ? (inner % k.W == 0) : false;
         };
         for (const auto& name : preferred)
             for (size_t i = 0; i < v.size(); ++i)
                 if (name == v[i].name && ok(v[i])) return (int)i;
         for (size_t i = 0; i < v.size(); ++i)
             if (ok(v[i])) return (int)i;
-        if (!contiguous)   // narrow inner dimension: fall back to one column per tile (strided, uncoalesced)
-            for (size_t i = 0; i < v.size(); ++i)
-                if (v[i].prec == prec && v[i].log2n == log2n && v[i].W == 1) return (int)i;
+        if (!contiguous) return pick_direct_w1(prec, log2n);   // narrow inner dimension: one column per tile
+        return -1;
+    }
+    // first plain (non-TMA) W = 1 variant: strided fallback, and the fallback for unaligned pointers
+    int pick_direct_w1(int prec, int log2n) {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].prec == prec && v[i].log2n == log2n && v[i].W == 1 && v[i].kind == 0) return (int)i;
         return -1;
     }
     cudaError_t prepare(int idx) {
@@ -147,12 +161,14 @@ int ilog2ll(long long v) {
 
 struct Pass {
     int variant;
+    int fallback;          // plain variant used when a TMA variant's 16-byte alignment rule is not met
     int axis;              // 0 = x, 1 = y, 2 = z
     int log2n;
     long long n;
     long long inner;       // element stride of the transformed axis
     long long outer;       // lines groups per transform: number of [n][inner] blocks per single transform
     const void* tw[3];
+    const void* tw_fb[3];  // twiddle tables of the fallback variant (its radices may differ)
 };
 
 }  // namespace
@@ -186,6 +202,8 @@ int build_passes(b2fft_plan* pl) {
         const KernelVariant& kv = reg.v[vi];
         Pass p{};
         p.variant = vi;
+        p.fallback = kv.kind == 0 ? vi : reg.pick_direct_w1(pl->prec, lg);
+        if (p.fallback < 0) return fail(B2FFT_E_UNSUPPORTED, "no fallback kernel for axis %c", "xyz"[a]);
         p.axis = a;
         p.log2n = lg;
         p.n = dims[a];
@@ -199,6 +217,19 @@ int build_passes(b2fft_plan* pl) {
         }
         cudaError_t e = reg.prepare(vi);
         if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+        if (p.fallback != vi) {
+            const KernelVariant& fb = reg.v[p.fallback];
+            NS = (int)dims[a];
+            for (int s = 0; s + 1 < fb.S; ++s) {
+                int rc = twiddles().get(pl->device, pl->prec, NS, fb.radix[s], &p.tw_fb[s]);
+                if (rc) return rc;
+                NS /= fb.radix[s];
+            }
+            e = reg.prepare(p.fallback);
+            if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+        } else {
+            for (int s = 0; s < 3; ++s) p.tw_fb[s] = p.tw[s];
+        }
         pl->passes.push_back(p);
     }
     return 0;
@@ -206,20 +237,24 @@ int build_passes(b2fft_plan* pl) {
 
 template <typename T>
 int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1, void* out0, void* out1, int inverse,
-                long long batch, bool last, cudaStream_t stream) {
-    const KernelVariant& kv = registry().v[ps.variant];
-    b2::PassParams<T> p{};
+                long long outer_count, bool last, cudaStream_t stream) {
     const bool split = pl->layout == B2FFT_SPLIT;
+    int vi = ps.variant;
+    if (registry().v[vi].kind == 1) {   // TMA bulk copies need 16-byte aligned sources
+        if (((uintptr_t)in0 % 16) != 0 || (split && ((uintptr_t)in1 % 16) != 0)) vi = ps.fallback;
+    }
+    const KernelVariant& kv = registry().v[vi];
+    b2::PassParams<T> p{};
     if (split && inverse) {   // IDFT(z) = swap(DFT(swap(z))): swap the planes instead of the registers
         p.in0 = (const T*)in1; p.in1 = (const T*)in0; p.out0 = (T*)out1; p.out1 = (T*)out0;
     } else {
         p.in0 = (const T*)in0; p.in1 = (const T*)in1; p.out0 = (T*)out0; p.out1 = (T*)out1;
     }
-    for (int s = 0; s < 3; ++s) p.tw[s] = (const T*)ps.tw[s];
+    for (int s = 0; s < 3; ++s) p.tw[s] = (const T*)(vi == ps.variant ? ps.tw[s] : ps.tw_fb[s]);
     p.inner = ps.inner;
     p.inner_blocks = ps.inner / kv.W;
     p.outer_stride = ps.n * ps.inner;
-    p.n_tiles = batch * ps.outer * p.inner_blocks;
+    p.n_tiles = outer_count * p.inner_blocks;
     p.scale = (T)1;
     p.scale_mode = 0;
     if (last && pl->apply_scale) {
@@ -319,16 +354,61 @@ int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0
         }
         return B2FFT_OK;
     }
-    const void* ci0 = in0;
-    const void* ci1 = in1;
-    for (size_t i = 0; i < plan->passes.size(); ++i) {
-        const bool last = i + 1 == plan->passes.size();
-        int rc = plan->prec == B2FFT_F32
-                     ? launch_pass<float>(plan, plan->passes[i], ci0, ci1, out0, out1, inverse, batch, last, stream)
-                     : launch_pass<double>(plan, plan->passes[i], ci0, ci1, out0, out1, inverse, batch, last, stream);
-        if (rc) return rc;
-        ci0 = out0;   // later passes run in place on the output
-        ci1 = out1;
+    // ---- schedule: which consecutive passes share an L2-resident chunk
+    // unit = the smallest block of data that the passes of a group never leave: a whole transform
+    // ("volume") when it fits the L2 budget, else an XY plane for the X+Y passes (Z then runs alone).
+    const size_t csize = (size_t)(plan->prec ? 16 : 8);
+    const long long plane_elems = plan->x * plan->y, vol_elems = plane_elems * plan->z;
+    const long long budget = g_l2_chunk_bytes.load();
+    const size_t np = plan->passes.size();
+    struct Group { size_t first, last; long long unit_elems, units, chunk_units; };
+    Group groups[3];
+    int ng = 0;
+    const bool out_of_place = (in0 != out0);
+    // out-of-place streams the input through L2 as well: halve the resident chunk
+    const long long eff_budget = out_of_place ? budget / 2 : budget;
+    if (np >= 2 && eff_budget > 0 && (long long)(vol_elems * csize) <= eff_budget) {
+        const long long cu = eff_budget / (long long)(vol_elems * csize);
+        groups[ng++] = {0, np - 1, vol_elems, batch, cu < 1 ? 1 : cu};
+    } else if (np >= 2 && eff_budget > 0 && plan->passes[0].axis == 0 && plan->passes[1].axis == 1 &&
+               (long long)(plane_elems * csize) <= eff_budget) {
+        const long long cu = eff_budget / (long long)(plane_elems * csize);
+        groups[ng++] = {0, 1, plane_elems, batch * plan->z, cu < 1 ? 1 : cu};
+        if (np == 3) groups[ng++] = {2, 2, vol_elems, batch, batch};
+    } else {
+        for (size_t i = 0; i < np; ++i) groups[ng++] = {i, i, vol_elems, batch, batch};
+    }
+    // a chunk that covers (nearly) everything gains nothing: run whole passes
+    for (int g = 0; g < ng; ++g)
+        if (groups[g].chunk_units * 2 > groups[g].units) groups[g].chunk_units = groups[g].units;
+
+    const size_t in_esz = split ? csize / 2 : csize;   // bytes per element of each plane pointer
+    auto off = [&](const void* ptr, long long elems) -> const void* {
+        return ptr ? (const void*)((const char*)ptr + (size_t)elems * in_esz) : nullptr;
+    };
+    bool first_group = true;
+    for (int g = 0; g < ng; ++g) {
+        const Group& gr = groups[g];
+        for (long long u0 = 0; u0 < gr.units; u0 += gr.chunk_units) {
+            const long long nu = (gr.units - u0 < gr.chunk_units) ? gr.units - u0 : gr.chunk_units;
+            const long long eoff = u0 * gr.unit_elems;
+            for (size_t i = gr.first; i <= gr.last; ++i) {
+                const Pass& ps = plan->passes[i];
+                const bool from_input = first_group && i == gr.first;
+                const void* ci0 = off(from_input ? in0 : out0, eoff);
+                const void* ci1 = off(from_input ? in1 : out1, eoff);
+                void* co0 = (void*)off(out0, eoff);
+                void* co1 = (void*)off(out1, eoff);
+                // number of [n][inner] blocks of this pass inside nu units
+                const long long blocks = nu * (gr.unit_elems / (ps.n * ps.inner));
+                const bool last = i + 1 == np;
+                int rc = plan->prec == B2FFT_F32
+                             ? launch_pass<float>(plan, ps, ci0, ci1, co0, co1, inverse, blocks, last, stream)
+                             : launch_pass<double>(plan, ps, ci0, ci1, co0, co1, inverse, blocks, last, stream);
+                if (rc) return rc;
+            }
+        }
+        first_group = false;
     }
     return B2FFT_OK;
 }
@@ -386,7 +466,7 @@ int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, v
     b2fft_plan tmp;   // only used for bookkeeping of launch_pass
     tmp.prec = k.prec; tmp.layout = split ? B2FFT_SPLIT : B2FFT_INTERLEAVED; tmp.apply_scale = 0; tmp.device = device;
     Pass p{};
-    p.variant = index; p.log2n = k.log2n; p.n = 1LL << k.log2n; p.inner = inner;
+    p.variant = index; p.fallback = index; p.log2n = k.log2n; p.n = 1LL << k.log2n; p.inner = inner;
     int NS = (int)p.n;
     for (int s = 0; s + 1 < k.S; ++s) {
         int rc = twiddles().get(device, k.prec, NS, k.radix[s], &p.tw[s]);
@@ -395,13 +475,22 @@ int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, v
     }
     cudaError_t e = reg.prepare(index);
     if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
-    // launch_pass computes n_tiles = batch * outer * inner_blocks; fold everything into `outer`
     const long long inner_blocks = inner / k.W;
     if (n_tiles % inner_blocks != 0) return fail(B2FFT_E_INVALID, "n_tiles must be a multiple of inner/W");
     p.outer = n_tiles / inner_blocks;
     return k.prec == B2FFT_F32
-               ? launch_pass<float>(&tmp, p, in0, in1, out0, out1, inverse, 1, false, (cudaStream_t)cuda_stream)
-               : launch_pass<double>(&tmp, p, in0, in1, out0, out1, inverse, 1, false, (cudaStream_t)cuda_stream);
+               ? launch_pass<float>(&tmp, p, in0, in1, out0, out1, inverse, p.outer, false, (cudaStream_t)cuda_stream)
+               : launch_pass<double>(&tmp, p, in0, in1, out0, out1, inverse, p.outer, false, (cudaStream_t)cuda_stream);
+}
+
+int b2fft_set_option(const char* key, double value) {
+    if (!key) return fail(B2FFT_E_INVALID, "null key");
+    if (!strcmp(key, "l2_chunk_bytes")) {
+        if (value < 0) return fail(B2FFT_E_INVALID, "l2_chunk_bytes must be >= 0");
+        g_l2_chunk_bytes.store((long long)value);
+        return B2FFT_OK;
+    }
+    return fail(B2FFT_E_INVALID, "unknown option %s", key);
 }
 
 int b2fft_set_preferred_variants(const char* names) {

@@ -247,6 +247,34 @@ struct TileThread {
         }
     }
 
+    // ---- stage 0 input from a shared-memory staging buffer filled by TMA (persistent kernels):
+    //      the buffer holds the CTA's G tiles densely, tile g at g*N*W, element (n, w) at n*W + w.
+    //      SPLIT: `sre`/`sim` are two planes of T; interleaved: `sre` is a vec2<T> array, `sim` unused.
+    B2_HD void load_smem(const void* sre, const void* sim) {
+        if (!active) {
+            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] = 0; im[decltype(jc)::value] = 0; });
+            return;
+        }
+        const long long off = ((long long)g * N + t) * W + w;
+        if constexpr (SPLIT) {
+            const T* pr = static_cast<const T*>(sre) + off;
+            const T* pi = static_cast<const T*>(sim) + off;
+            static_for<0, E>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                re[j] = pr[j * TPC * W];
+                im[j] = pi[j * TPC * W];
+            });
+        } else {
+            const T2* pc = static_cast<const T2*>(sre) + off;
+            static_for<0, E>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const T2 v = pc[j * TPC * W];
+                if constexpr (INV) { re[j] = v.y; im[j] = v.x; }
+                else { re[j] = v.x; im[j] = v.y; }
+            });
+        }
+    }
+
     // ---- butterflies of stage s, then the stage twiddle (not after the last stage)
     template <int s>
     B2_HD void compute(const PassParams<T>& p) {

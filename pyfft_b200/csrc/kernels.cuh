@@ -34,6 +34,104 @@ tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
     th.store(p);
 }
 
+// ------------------------------------------------------------------ persistent TMA-fed kernel (contiguous axis)
+// One CTA per resident slot loops over groups of G transforms.  The next group's input is
+// fetched by a single cp.async.bulk (TMA 1D bulk copy, SASS UBLKCP) into a shared-memory ring
+// while the current group is in registers, so HBM reads stay in flight for the whole compute
+// phase instead of only during each CTA's load phase (the plain kernel is latency-bound at
+// 3-4 CTAs/SM, see profiles/).  Stage 0 then reads its elements from shared memory.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+template <class Cfg, int NBUF>
+struct TmaRowLayout {
+    using T = typename Cfg::T;
+    static constexpr size_t IN_BYTES = (size_t)Cfg::G * Cfg::N * 2 * sizeof(T);          // one ring slot (re+im)
+    static constexpr size_t X_OFF = NBUF * IN_BYTES;
+    static constexpr size_t X_BYTES = ((size_t)Cfg::SMEM_BYTES + 127) / 128 * 128;
+    static constexpr size_t BAR_OFF = X_OFF + X_BYTES;
+    static constexpr size_t TOTAL = BAR_OFF + 8 * NBUF;
+};
+
+template <class Cfg, bool SPLIT, bool INV, int MINB, int NBUF>
+__global__ void __launch_bounds__(Cfg::THREADS, MINB)
+tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    using L = TmaRowLayout<Cfg, NBUF>;
+    static_assert(Cfg::W == 1, "bulk-copy staging is for the contiguous axis");
+    extern __shared__ __align__(128) unsigned char b2_smem_raw[];
+    T2* xbuf = reinterpret_cast<T2*>(b2_smem_raw + L::X_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b2_smem_raw + L::BAR_OFF);
+    const int tid = (int)threadIdx.x;
+    const long long n_groups = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    const long long stride = gridDim.x;
+
+    // one elected thread fetches group `grp` into ring slot `slot`
+    auto issue = [&](long long grp, int slot) {
+        if (grp >= n_groups) return;
+        long long tiles = p.n_tiles - grp * Cfg::G;
+        if (tiles > Cfg::G) tiles = Cfg::G;
+        const long long first = grp * Cfg::G * Cfg::N;                     // element offset of the group
+        unsigned char* dst = b2_smem_raw + (size_t)slot * L::IN_BYTES;
+        if constexpr (SPLIT) {
+            const uint32_t bytes = (uint32_t)(tiles * Cfg::N * sizeof(T));
+            mbar_expect_tx(&bars[slot], 2 * bytes);
+            bulk_load(dst, p.in0 + first, bytes, &bars[slot]);
+            bulk_load(dst + L::IN_BYTES / 2, p.in1 + first, bytes, &bars[slot]);
+        } else {
+            const uint32_t bytes = (uint32_t)(tiles * Cfg::N * 2 * sizeof(T));
+            mbar_expect_tx(&bars[slot], bytes);
+            bulk_load(dst, reinterpret_cast<const T2*>(p.in0) + first, bytes, &bars[slot]);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) mbar_init(&bars[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long grp = blockIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) issue(grp + b * stride, b);
+    }
+    TileThread<Cfg, SPLIT, INV> th;
+    for (unsigned it = 0; grp < n_groups; ++it, grp += stride) {
+        const int slot = (int)(it % NBUF);
+        th.setup(tid, grp, p);
+        mbar_wait(&bars[slot], (it / NBUF) & 1);
+        const unsigned char* src = b2_smem_raw + (size_t)slot * L::IN_BYTES;
+        th.load_smem(src, src + L::IN_BYTES / 2);
+        __syncthreads();                       // slot fully consumed (and the previous exchange fully read)
+        if (tid == 0) issue(grp + (long long)NBUF * stride, slot);
+        run_stages<Cfg, SPLIT, INV, 0>(th, p, xbuf);
+        th.store(p);
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -44,6 +142,8 @@ struct KernelVariant {
     int threads;
     long long smem_bytes;
     int minb;
+    int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis only)
+    int nbuf;        // ring depth for kind 1
     // launches ceil(n_tiles / G) CTAs; params points at a PassParams<T> of the right T
     cudaError_t (*launch)(int split, int inv, const void* params, cudaStream_t stream);
     cudaError_t (*prepare)();   // one-time function attributes (dynamic smem opt-in)
@@ -102,6 +202,65 @@ struct VariantOps {
     }
 };
 
+template <class Cfg, int MINB, int NBUF>
+struct VariantOpsTma {
+    using T = typename Cfg::T;
+    using L = TmaRowLayout<Cfg, NBUF>;
+    static int& slots() { static int s = 0; return s; }   // resident CTAs on the device (SMs x occupancy)
+    static cudaError_t prepare() {
+        const int b = (int)L::TOTAL;
+        cudaError_t e = cudaFuncSetAttribute(tile_fft_kernel_tma_row<Cfg, false, false, MINB, NBUF>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_fft_kernel_tma_row<Cfg, false, true, MINB, NBUF>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tile_fft_kernel_tma_row<Cfg, true, false, MINB, NBUF>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_fft_kernel_tma_row<Cfg, false, false, MINB, NBUF>,
+                                                          Cfg::THREADS, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return cudaSuccess;
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+        if (ctas <= 0) return cudaSuccess;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        if (ctas > slots()) ctas = slots();
+        const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
+        const size_t sm = L::TOTAL;
+        if (split) tile_fft_kernel_tma_row<Cfg, true, false, MINB, NBUF><<<grid, block, sm, stream>>>(p);
+        else if (inv) tile_fft_kernel_tma_row<Cfg, false, true, MINB, NBUF><<<grid, block, sm, stream>>>(p);
+        else tile_fft_kernel_tma_row<Cfg, false, false, MINB, NBUF><<<grid, block, sm, stream>>>(p);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_fft_kernel_tma_row<Cfg, false, false, MINB, NBUF>,
+                                                          Cfg::THREADS, L::TOTAL) != cudaSuccess)
+            return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v = VariantOps<Cfg, MINB>::make(name);
+        v.smem_bytes = (long long)L::TOTAL;
+        v.kind = 1;
+        v.nbuf = NBUF;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        return v;
+    }
+};
+
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x
 #define B2_STR(x) B2_STR2(x)
@@ -109,9 +268,15 @@ struct VariantOps {
     out.push_back(::b2::VariantOps<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB>::make(               \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3)));
 
+// B2_VT(type, log2n, G, minblocks, ring depth, R0, R1, R2, R3): persistent TMA-staged contiguous-axis variant
+#define B2_VT(T, L, G, MB, NB, R0, R1, R2, R3)                                                       \
+    out.push_back(::b2::VariantOpsTma<::b2::TileCfg<T, L, 1, G, R0, R1, R2, R3>, MB, NB>::make(        \
+        #T "_n" B2_STR(L) "_w1_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tma" B2_STR(NB)));
+
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);
 void register_f64_row(std::vector<KernelVariant>& out);
 void register_f64_col(std::vector<KernelVariant>& out);
+void register_exp(std::vector<KernelVariant>& out);
 
 }  // namespace b2

@@ -1,0 +1,13 @@
+// Kernel instantiations for group EXP (see variants.def).
+#include "kernels.cuh"
+
+namespace b2 {
+void register_exp(std::vector<KernelVariant>& out) {
+#define B2_GROUP_EXP
+#define X B2_V
+#define XT B2_VT
+#include "variants.def"
+#undef X
+#undef XT
+}
+}  // namespace b2

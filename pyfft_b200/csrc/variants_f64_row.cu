@@ -5,7 +5,9 @@ namespace b2 {
 void register_f64_row(std::vector<KernelVariant>& out) {
 #define B2_GROUP_F64_ROW
 #define X B2_V
+#define XT B2_VT
 #include "variants.def"
 #undef X
+#undef XT
 }
 }  // namespace b2

@@ -51,7 +51,7 @@ static void emu_stages(std::vector<TileThread<Cfg, SPLIT, INV>>& th, const PassP
 
 // Runs one pass over an [outer][N][inner] array and returns the max relative error.
 template <class Cfg, bool SPLIT, bool INV>
-static double run_case(long long outer, long long inner, unsigned seed) {
+static double run_case(long long outer, long long inner, unsigned seed, bool staged = false) {
     using T = typename Cfg::T;
     using T2 = vec2<T>;
     const int N = Cfg::N;
@@ -82,7 +82,22 @@ static double run_case(long long outer, long long inner, unsigned seed) {
     std::vector<T2> smem((size_t)Cfg::COL_SMEM * Cfg::W * Cfg::G + 1);
     for (long long bid = 0; bid < ctas; ++bid) {
         std::vector<TileThread<Cfg, SPLIT, INV>> th(Cfg::THREADS);
-        for (int tid = 0; tid < Cfg::THREADS; ++tid) { th[tid].setup(tid, bid, p); th[tid].load(p); }
+        // staged = the persistent TMA kernels' path: the group's input is bulk-copied to "shared
+        // memory" (dense, tile g at g*N*W) and stage 0 reads it from there via load_smem()
+        std::vector<T2> st_c((size_t)Cfg::G * N * Cfg::W);
+        std::vector<T> st_re((size_t)Cfg::G * N * Cfg::W), st_im((size_t)Cfg::G * N * Cfg::W);
+        if (staged) {
+            long long tiles = p.n_tiles - bid * Cfg::G;
+            if (tiles > Cfg::G) tiles = Cfg::G;
+            const long long first = bid * Cfg::G * N, cnt = tiles * N;     // W == 1, inner == 1
+            for (long long i = 0; i < cnt; ++i) { st_c[i] = in_c[first + i]; st_re[i] = in_re[first + i]; st_im[i] = in_im[first + i]; }
+        }
+        for (int tid = 0; tid < Cfg::THREADS; ++tid) {
+            th[tid].setup(tid, bid, p);
+            if (!staged) th[tid].load(p);
+            else if (SPLIT) th[tid].load_smem(st_re.data(), st_im.data());
+            else th[tid].load_smem(st_c.data(), nullptr);
+        }
         emu_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
         for (auto& t : th) t.store(p);
     }
@@ -126,6 +141,21 @@ static void check(const char* name, long long outer, long long inner) {
                 e0, e1, e2, (long long)Cfg::SMEM_BYTES, Cfg::THREADS, ok ? "ok" : "FAIL");
     if (!ok) ++g_fail;
 }
+
+template <class Cfg>
+static void check_staged(const char* name, long long outer) {
+    using T = typename Cfg::T;
+    const double tol = sizeof(T) == 4 ? 3e-6 : 1e-14;
+    double e0 = run_case<Cfg, false, false>(outer, 1, 4, true);
+    double e1 = run_case<Cfg, false, true>(outer, 1, 5, true);
+    double e2 = run_case<Cfg, true, false>(outer, 1, 6, true);
+    bool ok = e0 < tol && e1 < tol && e2 < tol;
+    std::printf("%-44s outer=%lld staged   err fwd=%.2e inv=%.2e split=%.2e %s\n", name, outer, e0, e1, e2, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
+#define CHKT(T, L, G, R0, R1, R2, R3) \
+    check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
 
 #define CHK(T, L, W, G, R0, R1, R2, R3, OUTER, INNER) \
     check<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER);
