@@ -88,6 +88,26 @@ B2FFT_API int b2fft_plan_set_workspace(b2fft_plan* plan, void* dptr, size_t byte
 B2FFT_API int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0, void* out1, int inverse,
                   int64_t batch, void* cuda_stream);
 
+/* Slab-decomposed multi-GPU transforms (no reference counterpart).  Makes the
+ * plan's LAST pass write its output destination-blocked: the transformed axis (length n) is cut
+ * into nblocks equal blocks and output index k goes to block h = k / (n/nblocks), element
+ *     blk0[h][ outer*out_outer_stride + inner_index + (k % (n/nblocks)) * out_inner ]
+ * (blk1 = imaginary planes for the split layout).  Block pointers may be local send-buffer
+ * chunks (followed by an NCCL all-to-all) or peer GPUs' receive buffers mapped over NVLink, in
+ * which case the pass's stores ARE the exchange.  out0/out1 of b2fft_execute are then ignored
+ * for that pass.  nblocks = 0 restores plain output. */
+B2FFT_API int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk0, void* const* blk1,
+                                 int64_t out_inner, int64_t out_outer_stride);
+
+/* Peer-visible device memory for the slab exchange: plain cudaMalloc'ed buffers whose CUDA IPC
+ * handles (64 bytes) can be exchanged between the per-GPU processes (e.g. through
+ * torch.distributed.all_gather_object) and opened on the other ranks. */
+B2FFT_API int b2fft_mem_alloc(size_t bytes, int device, void** out);
+B2FFT_API int b2fft_mem_free(void* dptr);
+B2FFT_API int b2fft_ipc_export(void* dptr, unsigned char handle[64]);
+B2FFT_API int b2fft_ipc_import(const unsigned char handle[64], int device, void** out);
+B2FFT_API int b2fft_ipc_release(void* dptr);
+
 B2FFT_API int b2fft_plan_destroy(b2fft_plan* plan);
 
 /* Replaces Context.wait (pyfft/cuda.py:98-101): blocks until the stream has drained.  Only

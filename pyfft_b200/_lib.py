@@ -30,6 +30,12 @@ SIGNATURES = {
     "b2fft_plan_set_workspace": (_i, [_vp, _vp, _sz]),
     "b2fft_execute": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "b2fft_plan_destroy": (_i, [_vp]),
+    "b2fft_plan_set_output_blocks": (_i, [_vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _i64]),
+    "b2fft_mem_alloc": (_i, [_sz, _i, ctypes.POINTER(_vp)]),
+    "b2fft_mem_free": (_i, [_vp]),
+    "b2fft_ipc_export": (_i, [_vp, ctypes.c_char_p]),
+    "b2fft_ipc_import": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(_vp)]),
+    "b2fft_ipc_release": (_i, [_vp]),
     "b2fft_stream_synchronize": (_i, [_vp]),
     "b2fft_plan_num_passes": (_i, [_vp]),
     "b2fft_plan_describe": (_i, [_vp, ctypes.c_char_p, _sz]),

@@ -182,6 +182,11 @@ struct b2fft_plan {
     std::vector<Pass> passes;
     void* workspace = nullptr;
     size_t workspace_bytes = 0;
+    // destination-blocked output of the last pass (slab exchange), see b2fft_plan_set_output_blocks
+    int nblocks = 0;
+    void* blk0[B2_MAX_BLOCKS] = {};
+    void* blk1[B2_MAX_BLOCKS] = {};
+    long long blk_out_inner = 0, blk_out_outer_stride = 0;
     std::atomic<long long> launches{0};
 };
 
@@ -255,6 +260,21 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
     p.inner_blocks = ps.inner / kv.W;
     p.outer_stride = ps.n * ps.inner;
     p.n_tiles = outer_count * p.inner_blocks;
+    p.out_inner = p.inner;
+    p.out_outer_stride = p.outer_stride;
+    p.out_blk_log2 = -1;
+    if (last && pl->nblocks > 0) {
+        if (!kv.blk) return fail(B2FFT_E_UNSUPPORTED, "kernel %s has no destination-blocked store", kv.name);
+        if (ps.n % pl->nblocks) return fail(B2FFT_E_INVALID, "last axis length %lld not divisible into %d blocks", ps.n, pl->nblocks);
+        p.out_blk_log2 = ilog2ll(ps.n / pl->nblocks);
+        p.out_inner = pl->blk_out_inner;
+        p.out_outer_stride = pl->blk_out_outer_stride;
+        const bool sw = split && inverse;
+        for (int h = 0; h < pl->nblocks; ++h) {
+            p.out_blk0[h] = (T*)(sw ? pl->blk1[h] : pl->blk0[h]);
+            p.out_blk1[h] = (T*)(sw ? pl->blk0[h] : pl->blk1[h]);
+        }
+    }
     p.scale = (T)1;
     p.scale_mode = 0;
     if (last && pl->apply_scale) {
@@ -334,7 +354,8 @@ int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0
     if (!plan) return fail(B2FFT_E_INVALID, "null plan");
     if (batch < 0) return fail(B2FFT_E_INVALID, "negative batch");
     const bool split = plan->layout == B2FFT_SPLIT;
-    if (!in0 || !out0 || (split && (!in1 || !out1))) return fail(B2FFT_E_INVALID, "null data pointer");
+    if (!in0 || (split && !in1)) return fail(B2FFT_E_INVALID, "null data pointer");
+    if (!out0 || (split && !out1)) return fail(B2FFT_E_INVALID, "null data pointer");
     const size_t align = split ? (plan->prec ? 8 : 4) : (plan->prec ? 16 : 8);
     const void* ptrs[4] = {in0, in1, out0, out1};
     for (int i = 0; i < 4; ++i)
@@ -359,7 +380,7 @@ int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0
     // ("volume") when it fits the L2 budget, else an XY plane for the X+Y passes (Z then runs alone).
     const size_t csize = (size_t)(plan->prec ? 16 : 8);
     const long long plane_elems = plan->x * plan->y, vol_elems = plane_elems * plan->z;
-    const long long budget = g_l2_chunk_bytes.load();
+    const long long budget = plan->nblocks > 0 ? 0 : g_l2_chunk_bytes.load();
     const size_t np = plan->passes.size();
     struct Group { size_t first, last; long long unit_elems, units, chunk_units; };
     Group groups[3];
@@ -410,6 +431,66 @@ int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0
         }
         first_group = false;
     }
+    return B2FFT_OK;
+}
+
+int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk0, void* const* blk1,
+                                 int64_t out_inner, int64_t out_outer_stride) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (nblocks == 0) { plan->nblocks = 0; return B2FFT_OK; }
+    if (nblocks < 0 || nblocks > B2_MAX_BLOCKS || (nblocks & (nblocks - 1)))
+        return fail(B2FFT_E_INVALID, "nblocks must be a power of two <= %d", B2_MAX_BLOCKS);
+    if (plan->passes.empty()) return fail(B2FFT_E_INVALID, "plan has no pass to re-layout");
+    const bool split = plan->layout == B2FFT_SPLIT;
+    if (!blk0 || (split && !blk1)) return fail(B2FFT_E_INVALID, "null block pointer table");
+    const Pass& lastp = plan->passes.back();
+    if (lastp.n % nblocks) return fail(B2FFT_E_INVALID, "axis length %lld not divisible by %d", lastp.n, nblocks);
+    if (!registry().v[lastp.variant].blk)
+        return fail(B2FFT_E_UNSUPPORTED, "kernel %s has no destination-blocked store", registry().v[lastp.variant].name);
+    for (int h = 0; h < nblocks; ++h) {
+        if (!blk0[h] || (split && !blk1[h])) return fail(B2FFT_E_INVALID, "null block pointer %d", h);
+        plan->blk0[h] = blk0[h];
+        plan->blk1[h] = split ? blk1[h] : nullptr;
+    }
+    plan->nblocks = nblocks;
+    plan->blk_out_inner = out_inner;
+    plan->blk_out_outer_stride = out_outer_stride;
+    return B2FFT_OK;
+}
+
+int b2fft_mem_alloc(size_t bytes, int device, void** out) {
+    if (!out) return fail(B2FFT_E_INVALID, "null argument");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(B2FFT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    CUDA_TRY(cudaMalloc(out, bytes));
+    return B2FFT_OK;
+}
+
+int b2fft_mem_free(void* dptr) {
+    CUDA_TRY(cudaFree(dptr));
+    return B2FFT_OK;
+}
+
+int b2fft_ipc_export(void* dptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, 64);
+    return B2FFT_OK;
+}
+
+int b2fft_ipc_import(const unsigned char handle[64], int device, void** out) {
+    if (!out) return fail(B2FFT_E_INVALID, "null argument");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(B2FFT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B2FFT_OK;
+}
+
+int b2fft_ipc_release(void* dptr) {
+    CUDA_TRY(cudaIpcCloseMemHandle(dptr));
     return B2FFT_OK;
 }
 

@@ -110,6 +110,7 @@ B2_HD void butterfly(T* re, T* im) {
 }
 
 // ------------------------------------------------------------------ pass parameters
+#define B2_MAX_BLOCKS 16
 template <typename T>
 struct PassParams {
     const T* in0;   // interleaved: vec2<T>* ; split: re plane
@@ -121,8 +122,17 @@ struct PassParams {
     long long inner;         // element stride between consecutive n (1 for the contiguous axis)
     long long inner_blocks;  // inner / W
     long long outer_stride;  // N * inner
+    // output side (equal to the input side unless the pass re-lays-out its result)
+    long long out_inner;         // element stride between consecutive n in the output
+    long long out_outer_stride;  // element stride between consecutive outer blocks in the output
     T scale;                 // multiplier (scale_mode 1) or divisor (scale_mode 2)
     int scale_mode;          // 0: none
+    // destination-blocked stores (slab-decomposed multi-GPU transforms): output index n goes to
+    // block h = n >> out_blk_log2 at in-block position n & (2^out_blk_log2 - 1); block h lives at
+    // out_blk0[h] (+ out_blk1[h] for the split layout), which may be local or peer (NVLink) memory.
+    int out_blk_log2;        // < 0: plain stores to out0/out1
+    T* out_blk0[B2_MAX_BLOCKS];
+    T* out_blk1[B2_MAX_BLOCKS];
 };
 
 // ------------------------------------------------------------------ compile-time plan
@@ -206,7 +216,8 @@ struct TileThread {
     T re[E], im[E];
     int t, w, g;          // thread-in-column, column-in-tile, tile-in-CTA
     bool active;
-    long long base;       // element offset of (n = 0, this column)
+    long long base;       // element offset of (n = 0, this column) in the input
+    long long obase;      // ... and in the output
 
     B2_HD void setup(int tid, long long bid, const PassParams<T>& p) {
         w = tid % W;
@@ -218,6 +229,7 @@ struct TileThread {
         if (p.inner_blocks > 1) { o = tile / p.inner_blocks; ib = tile - o * p.inner_blocks; }
         else { o = tile; ib = 0; }
         base = o * p.outer_stride + ib * W + w;
+        obase = o * p.out_outer_stride + ib * W + w;
     }
 
     // ---- stage 0 input: element n = t + TPC*j  (BPT(0) == 1)
@@ -336,7 +348,9 @@ struct TileThread {
         });
     }
 
-    // ---- final output: n = t + TPC*(i + k*BPT) in natural order, scaled
+    // ---- final output: n = t + TPC*(i + k*BPT) in natural order, scaled.
+    //      BLK: destination-blocked stores (see PassParams::out_blk_log2).
+    template <bool BLK = false>
     B2_HD void store(const PassParams<T>& p) {
         if (!active) return;
         constexpr int s = S - 1;
@@ -346,10 +360,34 @@ struct TileThread {
         } else if (p.scale_mode == 2) {
             static_for<0, E>([&](auto jc) { re[decltype(jc)::value] /= p.scale; im[decltype(jc)::value] /= p.scale; });
         }
-        const long long step = (long long)TPC * p.inner;
+        if constexpr (BLK) {
+            const int lg = p.out_blk_log2;
+            const int mask = (1 << lg) - 1;
+            static_for<0, BPT>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                static_for<0, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int q = i * R + brev(k, LG);
+                    const int n = t + TPC * (i + k * BPT);
+                    const int h = n >> lg;
+                    const long long off = obase + (long long)(n & mask) * p.out_inner;
+                    if constexpr (SPLIT) {
+                        p.out_blk0[h][off] = re[q];
+                        p.out_blk1[h][off] = im[q];
+                    } else {
+                        T2 v;
+                        if constexpr (INV) { v.x = im[q]; v.y = re[q]; }
+                        else { v.x = re[q]; v.y = im[q]; }
+                        reinterpret_cast<T2*>(p.out_blk0[h])[off] = v;
+                    }
+                });
+            });
+            return;
+        }
+        const long long step = (long long)TPC * p.out_inner;
         if constexpr (SPLIT) {
-            T* pr = p.out0 + base + (long long)t * p.inner;
-            T* pi = p.out1 + base + (long long)t * p.inner;
+            T* pr = p.out0 + obase + (long long)t * p.out_inner;
+            T* pi = p.out1 + obase + (long long)t * p.out_inner;
             static_for<0, BPT>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 static_for<0, R>([&](auto kc) {
@@ -360,7 +398,7 @@ struct TileThread {
                 });
             });
         } else {
-            T2* pc = reinterpret_cast<T2*>(p.out0) + base + (long long)t * p.inner;
+            T2* pc = reinterpret_cast<T2*>(p.out0) + obase + (long long)t * p.out_inner;
             static_for<0, BPT>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 static_for<0, R>([&](auto kc) {

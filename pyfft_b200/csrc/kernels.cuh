@@ -22,7 +22,7 @@ __device__ __forceinline__ void run_stages(TileThread<Cfg, SPLIT, INV>& th, cons
     }
 }
 
-template <class Cfg, bool SPLIT, bool INV, int MINB>
+template <class Cfg, bool SPLIT, bool INV, int MINB, bool BLK = false>
 __global__ void __launch_bounds__(Cfg::THREADS, MINB)
 tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
     extern __shared__ __align__(16) unsigned char b2_smem_raw[];
@@ -31,7 +31,8 @@ tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
     th.setup((int)threadIdx.x, (long long)blockIdx.x, p);
     th.load(p);
     run_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
-    th.store(p);
+    th.template store<BLK>(p);
+    if constexpr (BLK) __threadfence_system();   // peer (NVLink) stores visible before the kernel retires
 }
 
 // ------------------------------------------------------------------ persistent TMA-fed kernel (contiguous axis)
@@ -144,6 +145,7 @@ struct KernelVariant {
     int minb;
     int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis only)
     int nbuf;        // ring depth for kind 1
+    int blk;         // 1: also compiled with destination-blocked stores (slab exchange passes)
     // launches ceil(n_tiles / G) CTAs; params points at a PassParams<T> of the right T
     cudaError_t (*launch)(int split, int inv, const void* params, cudaStream_t stream);
     cudaError_t (*prepare)();   // one-time function attributes (dynamic smem opt-in)
@@ -151,13 +153,21 @@ struct KernelVariant {
     int (*occupancy)();
 };
 
-template <class Cfg, int MINB>
+template <class Cfg, int MINB, bool BLKCAP = false>
 struct VariantOps {
     using T = typename Cfg::T;
     static cudaError_t prepare() {
         cudaError_t e = cudaSuccess;
         if (Cfg::SMEM_BYTES > 48 * 1024) {
             const int b = (int)Cfg::SMEM_BYTES;
+            if constexpr (BLKCAP) {
+                e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, false, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, true, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, true, false, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+                if (e != cudaSuccess) return e;
+            }
             e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
@@ -173,6 +183,16 @@ struct VariantOps {
         if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
         const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
         const size_t sm = (size_t)Cfg::SMEM_BYTES;
+        if (p.out_blk_log2 >= 0) {
+            if constexpr (BLKCAP) {
+                if (split) tile_fft_kernel<Cfg, true, false, MINB, true><<<grid, block, sm, stream>>>(p);
+                else if (inv) tile_fft_kernel<Cfg, false, true, MINB, true><<<grid, block, sm, stream>>>(p);
+                else tile_fft_kernel<Cfg, false, false, MINB, true><<<grid, block, sm, stream>>>(p);
+                return cudaGetLastError();
+            } else {
+                return cudaErrorNotSupported;
+            }
+        }
         if (split) tile_fft_kernel<Cfg, true, false, MINB><<<grid, block, sm, stream>>>(p);
         else if (inv) tile_fft_kernel<Cfg, false, true, MINB><<<grid, block, sm, stream>>>(p);
         else tile_fft_kernel<Cfg, false, false, MINB><<<grid, block, sm, stream>>>(p);
@@ -195,6 +215,7 @@ struct VariantOps {
         v.threads = Cfg::THREADS;
         v.smem_bytes = Cfg::SMEM_BYTES;
         v.minb = MINB;
+        v.blk = BLKCAP ? 1 : 0;
         v.launch = &launch;
         v.prepare = &prepare;
         v.occupancy = &occupancy;
@@ -250,7 +271,7 @@ struct VariantOpsTma {
         return n;
     }
     static KernelVariant make(const char* name) {
-        KernelVariant v = VariantOps<Cfg, MINB>::make(name);
+        KernelVariant v = VariantOps<Cfg, MINB, false>::make(name);
         v.smem_bytes = (long long)L::TOTAL;
         v.kind = 1;
         v.nbuf = NBUF;
@@ -266,6 +287,11 @@ struct VariantOpsTma {
 #define B2_STR(x) B2_STR2(x)
 #define B2_V(T, L, W, G, MB, R0, R1, R2, R3)                                                         \
     out.push_back(::b2::VariantOps<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB>::make(               \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3)));
+
+// B2_VB: like B2_V, additionally compiled with destination-blocked stores (used for the strided-axis defaults)
+#define B2_VB(T, L, W, G, MB, R0, R1, R2, R3)                                                        \
+    out.push_back(::b2::VariantOps<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, true>::make(         \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3)));
 
 // B2_VT(type, log2n, G, minblocks, ring depth, R0, R1, R2, R3): persistent TMA-staged contiguous-axis variant

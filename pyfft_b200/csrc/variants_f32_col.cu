@@ -4,7 +4,7 @@
 namespace b2 {
 void register_f32_col(std::vector<KernelVariant>& out) {
 #define B2_GROUP_F32_COL
-#define X B2_V
+#define X B2_VB
 #define XT B2_VT
 #include "variants.def"
 #undef X

@@ -1,0 +1,266 @@
+"""Multi-GPU execution: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The reference is single-device; both paths here are new functionality:
+
+* ``shard_batch`` / ``BatchShardedPlan`` -- independent transforms: the batch is split contiguously
+  over the ranks, every rank runs an ordinary ``Plan`` on its shard, no data-path collective.
+* ``SlabPlan`` -- one large 3D transform of a (Z, Y, X) array distributed as z-slabs.  Forward:
+  local X and Y passes, ONE exchange, local Z pass; the result is left y-slab distributed
+  ("transposed out": rank h holds ``[Z][Y/G][X]`` for its y range).  The exchange is fused into the
+  Y pass: its stores are destination-blocked (``b2fft_plan_set_output_blocks``) and, with
+  ``exchange="p2p"``, go straight into the peers' receive buffers over NVLink (CUDA IPC mapped), so
+  the transfer overlaps the butterflies tile by tile and no pack/unpack kernel exists.
+  ``exchange="nccl"`` is the baseline: blocked stores into a local send buffer followed by
+  ``all_to_all_single``.
+"""
+import ctypes
+
+import numpy
+
+from . import _lib
+from .plan import _NP_DTYPES, _resolve_dtype, _stream_handle
+
+
+# ----------------------------------------------------------------------------- batch sharding
+def shard_batch(batch, world_size, rank):
+    """Contiguous split of ``batch`` transforms: returns (first, count) for ``rank``."""
+    batch, world_size, rank = int(batch), int(world_size), int(rank)
+    if world_size < 1 or not 0 <= rank < world_size or batch < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(batch, world_size)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+class BatchShardedPlan(object):
+    """``Plan`` for a batch split over the ranks of a process group (no collective on the data path)."""
+
+    def __init__(self, shape, dtype=numpy.complex64, group=None, **plan_kwargs):
+        import torch.distributed as dist
+        from .cuda import Plan
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.plan = Plan(shape, dtype=dtype, **plan_kwargs)
+
+    def local_range(self, global_batch):
+        return shard_batch(global_batch, self.world, self.rank)
+
+    def execute(self, *buffers, **kw):
+        """Buffers hold this rank's shard; ``batch`` is the GLOBAL batch."""
+        global_batch = kw.pop("batch", 1)
+        _, count = self.local_range(global_batch)
+        if count == 0:
+            return None
+        return self.plan.execute(*buffers, batch=count, **kw)
+
+
+# ----------------------------------------------------------------------------- slab layout (pure host logic)
+def slab_layout(shape, world_size, rank):
+    """Index bookkeeping of the slab decomposition, in complex elements.
+
+    Rank g owns z in [g*Zl, (g+1)*Zl) as ``[Zl][Y][X]``; after the exchange rank h owns
+    y in [h*Yb, (h+1)*Yb) as ``[Z][Yb][X]``.
+    """
+    Z, Y, X = (int(s) for s in shape)
+    G = int(world_size)
+    if G < 1 or (G & (G - 1)):
+        raise ValueError("number of ranks must be a power of two")
+    if Z % G or Y % G:
+        raise ValueError("Z and Y must be divisible by the number of ranks")
+    Zl, Yb = Z // G, Y // G
+    return {
+        "Z": Z, "Y": Y, "X": X, "G": G, "Zl": Zl, "Yb": Yb,
+        "slab_elems": Zl * Y * X, "yslab_elems": Z * Yb * X, "block_elems": Zl * Yb * X,
+        # forward: Y pass of rank g writes y-block h to  recv_h + fwd_peer_offset  (P2P) or
+        #          send + h * block_elems (NCCL), rows of length X, planes Yb*X apart
+        "fwd_peer_offset": rank * Zl * Yb * X,
+        "fwd_out_inner": X, "fwd_out_outer_stride": Yb * X,
+        # inverse: Z pass of rank h writes z-block g to  slab_g + inv_peer_offset, z planes Y*X apart
+        "inv_peer_offset": rank * Yb * X,
+        "inv_out_inner": Y * X, "inv_out_outer_stride": 0,
+    }
+
+
+class _DeviceBuffer(object):
+    """cudaMalloc'ed buffer whose IPC handle can be shared with the other ranks."""
+
+    def __init__(self, nbytes, device):
+        self._lib = _lib.load()
+        self.nbytes = int(nbytes)
+        self.device = int(device)
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.b2fft_mem_alloc(self.nbytes, self.device, ctypes.byref(p)))
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def handle(self):
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(self._lib.b2fft_ipc_export(self.ptr, buf))
+        return buf.raw
+
+    def tensor(self, tdtype):
+        import torch
+        return torch.as_tensor(self, device="cuda:%d" % self.device).view(tdtype)
+
+    def free(self):
+        if self.ptr:
+            self._lib.b2fft_mem_free(self.ptr)
+            self.ptr = None
+
+
+def _open_peers(handles, my_rank, my_ptr, device):
+    lib = _lib.load()
+    ptrs = []
+    for r, h in enumerate(handles):
+        if r == my_rank:
+            ptrs.append(my_ptr)
+        else:
+            p = ctypes.c_void_p()
+            _lib.check(lib.b2fft_ipc_import(h, device, ctypes.byref(p)))
+            ptrs.append(p.value)
+    return ptrs
+
+
+class SlabPlan(object):
+    """Slab-decomposed 3D C2C FFT over the ranks of a torch.distributed (NCCL) group.
+
+    ``plan.slab``  : this rank's ``[Zl, Y, X]`` z-slab (input of ``forward``, output of ``inverse``)
+    ``plan.yslab`` : this rank's ``[Z, Yb, X]`` y-slab (output of ``forward``, input of ``inverse``)
+    Both are torch views of plan-owned, peer-visible device buffers; fill ``plan.slab`` in place.
+    """
+
+    def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
+                 exchange="p2p", device=None):
+        import torch
+        import torch.distributed as dist
+        if len(shape) != 3:
+            raise ValueError("SlabPlan needs a 3D shape (Z, Y, X)")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.exchange = exchange
+        self.dtype = _resolve_dtype(dtype)
+        if self.dtype.kind != "c":
+            raise ValueError("SlabPlan handles interleaved complex data")
+        self.prec, self.layout = _NP_DTYPES[self.dtype]
+        self.tdtype = torch.complex64 if self.dtype == numpy.complex64 else torch.complex128
+        self.esz = self.dtype.itemsize
+        L = self.L = slab_layout(shape, self.world, self.rank)
+        lib = self._lib = _lib.load()
+
+        def make(dims, axes, apply_scale):
+            h = ctypes.c_void_p()
+            d = (ctypes.c_int64 * 3)(*dims)
+            _lib.check(lib.b2fft_plan_create_ex(ctypes.byref(h), d, axes, self.prec, self.layout, int(bool(normalize)),
+                                                float(scale), int(bool(fast_math)), self.device,
+                                                float(L["X"]) * L["Y"] * L["Z"], int(apply_scale)))
+            return h
+
+        X, Y, Z, Zl, Yb = L["X"], L["Y"], L["Z"], L["Zl"], L["Yb"]
+        self._fwd_xy = make((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 0)     # forward: scale applied by the Z pass
+        self._fwd_z = make((X, Yb, Z), _lib.AXIS_Z, 1)
+        self._inv_z = make((X, Yb, Z), _lib.AXIS_Z, 0)                    # inverse: scale applied by the X/Y passes
+        self._inv_xy = make((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 1)
+
+        self._slab_buf = _DeviceBuffer(L["slab_elems"] * self.esz, self.device)
+        self._yslab_buf = _DeviceBuffer(L["yslab_elems"] * self.esz, self.device)
+        self.slab = self._slab_buf.tensor(self.tdtype).view(Zl, Y, X)
+        self.yslab = self._yslab_buf.tensor(self.tdtype).view(Z, Yb, X)
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+        self._send = None
+
+        G = self.world
+        if exchange == "p2p" and G > 1:
+            hs = [None] * G
+            dist.all_gather_object(hs, (self._slab_buf.handle(), self._yslab_buf.handle()), group=group)
+            self._peer_slab = _open_peers([h[0] for h in hs], self.rank, self._slab_buf.ptr, self.device)
+            self._peer_yslab = _open_peers([h[1] for h in hs], self.rank, self._yslab_buf.ptr, self.device)
+            fwd_ptrs = [p + L["fwd_peer_offset"] * self.esz for p in self._peer_yslab]
+            inv_ptrs = [p + L["inv_peer_offset"] * self.esz for p in self._peer_slab]
+            self._set_blocks(self._fwd_xy, fwd_ptrs, L["fwd_out_inner"], L["fwd_out_outer_stride"])
+            self._set_blocks(self._inv_z, inv_ptrs, L["inv_out_inner"], L["inv_out_outer_stride"])
+        elif G > 1:
+            self._send = torch.empty(L["slab_elems"], dtype=self.tdtype, device="cuda:%d" % self.device)
+            fwd_ptrs = [self._send.data_ptr() + h * L["block_elems"] * self.esz for h in range(G)]
+            self._set_blocks(self._fwd_xy, fwd_ptrs, L["fwd_out_inner"], L["fwd_out_outer_stride"])
+        else:
+            # single rank: the "exchange" is the Y pass writing into the y-slab buffer directly
+            self._set_blocks(self._fwd_xy, [self._yslab_buf.ptr], L["fwd_out_inner"], L["fwd_out_outer_stride"])
+            self._set_blocks(self._inv_z, [self._slab_buf.ptr], L["inv_out_inner"], L["inv_out_outer_stride"])
+
+    # ------------------------------------------------------------------ helpers
+    def _set_blocks(self, plan, ptrs, out_inner, out_outer_stride):
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        _lib.check(self._lib.b2fft_plan_set_output_blocks(plan, len(ptrs), arr, None, int(out_inner),
+                                                          int(out_outer_stride)))
+
+    def _exec(self, plan, src_ptr, dst_ptr, inverse):
+        stream = self._torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.b2fft_execute(plan, src_ptr, None, dst_ptr, None, int(inverse), 1, _stream_handle(stream)))
+
+    def _sync_ranks(self):
+        """Stream-ordered cross-rank barrier (tiny all-reduce; does not block the host)."""
+        if self.world > 1:
+            self._dist.all_reduce(self._flag, group=self.group)
+
+    @property
+    def launch_count(self):
+        return sum(int(self._lib.b2fft_plan_launch_count(p)) for p in (self._fwd_xy, self._fwd_z, self._inv_z, self._inv_xy))
+
+    # ------------------------------------------------------------------ transforms
+    def forward(self):
+        """``plan.slab`` (destroyed) -> ``plan.yslab``.  Asynchronous on the current stream."""
+        L, dist = self.L, self._dist
+        self._sync_ranks()                  # every rank is done with its previous y-slab contents
+        # X pass in place on the slab, then the Y pass whose stores are the exchange
+        self._exec(self._fwd_xy, self._slab_buf.ptr, self._slab_buf.ptr, 0)
+        if self.world > 1 and self.exchange == "nccl":
+            dist.all_to_all_single(self.yslab.view(-1), self._send, group=self.group)
+        else:
+            self._sync_ranks()              # all peers' blocks have landed in my y-slab
+        self._exec(self._fwd_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 0)
+        return self.yslab
+
+    def inverse(self):
+        """``plan.yslab`` (destroyed) -> ``plan.slab``."""
+        L, dist, torch = self.L, self._dist, self._torch
+        G = self.world
+        self._sync_ranks()
+        if G > 1 and self.exchange == "nccl":
+            self._exec(self._inv_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 1)
+            tmp = self._send
+            dist.all_to_all_single(tmp, self.yslab.view(-1), group=self.group)
+            # tmp = [h][Zl][Yb][X] -> slab [Zl][h*Yb + yl][X]
+            self.slab.view(L["Zl"], G, L["Yb"], L["X"]).copy_(
+                tmp.view(G, L["Zl"], L["Yb"], L["X"]).permute(1, 0, 2, 3))
+        else:
+            self._exec(self._inv_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 1)   # stores land in the peers' slabs
+            self._sync_ranks()
+        self._exec(self._inv_xy, self._slab_buf.ptr, self._slab_buf.ptr, 1)
+        return self.slab
+
+    def close(self):
+        for p in ("_fwd_xy", "_fwd_z", "_inv_z", "_inv_xy"):
+            h = getattr(self, p, None)
+            if h is not None:
+                self._lib.b2fft_plan_destroy(h)
+                setattr(self, p, None)
+        self.slab = self.yslab = None
+        if getattr(self, "_peer_slab", None):
+            for r, p in enumerate(self._peer_slab):
+                if r != self.rank:
+                    self._lib.b2fft_ipc_release(p)
+            for r, p in enumerate(self._peer_yslab):
+                if r != self.rank:
+                    self._lib.b2fft_ipc_release(p)
+            self._peer_slab = self._peer_yslab = None
+        for b in ("_slab_buf", "_yslab_buf"):
+            buf = getattr(self, b, None)
+            if buf is not None:
+                buf.free()

@@ -74,6 +74,9 @@ static double run_case(long long outer, long long inner, unsigned seed, bool sta
     p.inner_blocks = inner / Cfg::W;
     p.outer_stride = (long long)N * inner;
     p.n_tiles = outer * p.inner_blocks;
+    p.out_inner = inner;
+    p.out_outer_stride = (long long)N * inner;
+    p.out_blk_log2 = -1;
     p.scale = (T)0.5;
     p.scale_mode = 1;
     if (inner % Cfg::W != 0) { std::printf("bad inner\n"); std::exit(2); }
@@ -129,6 +132,62 @@ static double run_case(long long outer, long long inner, unsigned seed, bool sta
 
 static int g_fail = 0;
 
+// Destination-blocked stores (slab exchange): the transformed axis is cut into nblk blocks, block h
+// is written to its own buffer laid out [outer][N/nblk][inner].  Interleaved forward only.
+template <class Cfg>
+static void check_blocked(const char* name, long long outer, long long inner, int nblk) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    const int N = Cfg::N;
+    if (N % nblk) return;
+    const int blk = N / nblk;
+    const long long total = outer * N * inner;
+    std::mt19937_64 rng(77);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T2> in_c(total);
+    for (auto& v : in_c) { v.x = (T)nd(rng); v.y = (T)nd(rng); }
+    std::vector<std::vector<T2>> outb(nblk, std::vector<T2>((size_t)outer * blk * inner));
+    for (auto& b : outb) for (auto& v : b) { v.x = NAN; v.y = NAN; }
+    PassParams<T> p{};
+    std::vector<std::vector<T2>> tabs;
+    for (int s = 0; s + 1 < Cfg::S; ++s) tabs.push_back(make_stage_table<T>(Cfg::NS(s), Cfg::R(s)));
+    for (int s = 0; s + 1 < Cfg::S; ++s) p.tw[s] = reinterpret_cast<const T*>(tabs[s].data());
+    p.in0 = reinterpret_cast<const T*>(in_c.data());
+    p.inner = inner; p.inner_blocks = inner / Cfg::W; p.outer_stride = (long long)N * inner;
+    p.n_tiles = outer * p.inner_blocks;
+    p.out_inner = inner; p.out_outer_stride = (long long)blk * inner;
+    p.out_blk_log2 = ilog2(blk);
+    for (int h = 0; h < nblk; ++h) p.out_blk0[h] = reinterpret_cast<T*>(outb[h].data());
+    p.scale = 1; p.scale_mode = 0;
+    const long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    std::vector<T2> smem((size_t)Cfg::COL_SMEM * Cfg::W * Cfg::G + 1);
+    for (long long bid = 0; bid < ctas; ++bid) {
+        std::vector<TileThread<Cfg, false, false>> th(Cfg::THREADS);
+        for (int tid = 0; tid < Cfg::THREADS; ++tid) { th[tid].setup(tid, bid, p); th[tid].load(p); }
+        emu_stages<Cfg, false, false, 0>(th, p, smem);
+        for (auto& t : th) t.template store<true>(p);
+    }
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner; ++i) {
+            for (int n = 0; n < N; ++n) { auto v = in_c[(o * N + n) * inner + i]; line[n] = cld(v.x, v.y); }
+            ref_fft(line);
+            for (int n = 0; n < N; ++n) {
+                const T2 g = outb[n / blk][((size_t)o * blk + (n % blk)) * inner + i];
+                double e = (double)std::abs(cld(g.x, g.y) - line[n]);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(line[n]);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    const double tol = sizeof(T) == 4 ? 3e-6 : 1e-14;
+    const bool ok = max_err / max_mag < tol;
+    std::printf("%-44s outer=%lld inner=%lld blocked x%d err=%.2e %s\n", name, outer, inner, nblk, max_err / max_mag, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 template <class Cfg>
 static void check(const char* name, long long outer, long long inner) {
     using T = typename Cfg::T;
@@ -158,7 +217,8 @@ static void check_staged(const char* name, long long outer) {
     check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
 
 #define CHK(T, L, W, G, R0, R1, R2, R3, OUTER, INNER) \
-    check<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER);
+    check<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER); \
+    if ((W) > 1 && (L) >= 3) check_blocked<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER, (L) >= 8 ? 8 : 2);
 
 int main() {
 #include "emu_cases.inc"

@@ -1,0 +1,125 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: batch sharding and the slab
+decomposition's layout arithmetic.  The FFT compute is stood in for by numpy (test infrastructure);
+what is checked is that the block offsets / strides the CUDA Y pass is given (slab_layout) route
+every element to the right rank and position, in both exchange flavours."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pyfft_b200.dist import shard_batch, slab_layout
+
+
+def test_shard_batch_covers_everything():
+    for batch in (0, 1, 7, 8, 65536, 65537):
+        for world in (1, 2, 4, 8):
+            spans = [shard_batch(batch, world, r) for r in range(world)]
+            assert sum(c for _, c in spans) == batch
+            pos = 0
+            for first, count in spans:
+                assert first == pos
+                pos += count
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_batch(4, 2, 2)
+
+
+def test_slab_layout_rejects_bad_shapes():
+    with pytest.raises(ValueError):
+        slab_layout((6, 8, 8), 4, 0)
+    with pytest.raises(ValueError):
+        slab_layout((8, 8, 8), 3, 0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _blocked_store(L, yfft, send_or_peers, p2p):
+    """Emulates the Y pass's destination-blocked stores with the layout numbers the kernel gets."""
+    Zl, Y, X, Yb, G = L["Zl"], L["Y"], L["X"], L["Yb"], L["G"]
+    flat = yfft.reshape(Zl, Y, X)
+    for z in range(Zl):
+        for y in range(Y):
+            h, r = divmod(y, Yb)
+            base = z * L["fwd_out_outer_stride"] + r * L["fwd_out_inner"]
+            if p2p:
+                send_or_peers[h][L["fwd_peer_offset"] + base:L["fwd_peer_offset"] + base + X] = flat[z, y]
+            else:
+                send_or_peers[h * L["block_elems"] + base:h * L["block_elems"] + base + X] = flat[z, y]
+
+
+def _worker(rank, world, port, shape, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Z, Y, X = shape
+        L = slab_layout(shape, world, rank)
+        rng = np.random.default_rng(5)
+        full = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        want = np.fft.fftn(full)
+        slab = full[rank * L["Zl"]:(rank + 1) * L["Zl"]]
+        xy = np.fft.fft(np.fft.fft(slab, axis=2), axis=1)                 # local X and Y passes
+        # NCCL-flavoured exchange: blocked stores into a send buffer, then all_to_all
+        send = np.zeros(L["slab_elems"], dtype=np.complex128)
+        _blocked_store(L, xy, send, p2p=False)
+        st = torch.from_numpy(np.stack([send.real, send.imag], axis=1).copy())
+        rt = torch.empty_like(st)
+        dist.all_to_all_single(rt, st)
+        recv = (rt[:, 0] + 1j * rt[:, 1]).numpy().reshape(Z, L["Yb"], X)
+        got = np.fft.fft(recv, axis=0)                                    # local Z pass
+        ref = want[:, rank * L["Yb"]:(rank + 1) * L["Yb"], :]
+        err_nccl = float(np.abs(got - ref).max() / np.abs(ref).max())
+        # P2P-flavoured exchange: every rank's blocked stores applied to the peers' buffers; emulate by
+        # gathering all slabs and replaying each source rank's stores into this rank's buffer
+        gathered = [None] * world
+        dist.all_gather_object(gathered, xy)
+        mine = np.zeros(L["yslab_elems"], dtype=np.complex128)
+        for src in range(world):
+            Ls = slab_layout(shape, world, src)
+            bufs = [np.zeros(L["yslab_elems"], dtype=np.complex128) if h != rank else mine for h in range(world)]
+            _blocked_store(Ls, gathered[src], bufs, p2p=True)
+        got2 = np.fft.fft(mine.reshape(Z, L["Yb"], X), axis=0)
+        err_p2p = float(np.abs(got2 - ref).max() / np.abs(ref).max())
+        # inverse layout: z-block g of rank h's y-slab goes to slab_g + inv_peer_offset with stride Y*X
+        zinv = np.fft.ifft(want[:, rank * L["Yb"]:(rank + 1) * L["Yb"], :], axis=0)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, zinv)
+        myslab = np.zeros(L["slab_elems"], dtype=np.complex128)
+        for src in range(world):
+            Ls = slab_layout(shape, world, src)
+            blk = gathered[src][rank * L["Zl"]:(rank + 1) * L["Zl"]]      # [Zl][Yb][X] destined for me
+            for z in range(L["Zl"]):
+                for yl in range(L["Yb"]):
+                    off = Ls["inv_peer_offset"] + z * Ls["inv_out_inner"] + yl * X
+                    myslab[off:off + X] = blk[z, yl]
+        back = np.fft.ifft(np.fft.ifft(myslab.reshape(L["Zl"], Y, X), axis=1), axis=2)
+        err_inv = float(np.abs(back - slab).max())
+        q.put((rank, err_nccl, err_p2p, err_inv))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(8, 4, 16), (4, 8, 8)])
+def test_slab_exchange_layout_world2(shape):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, shape, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, e1, e2, e3 in res:
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (rank, e1, e2, e3)

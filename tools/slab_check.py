@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Slab-decomposed 3D FFT: correctness and timing under torchrun (one rank per GPU).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 \
+      tools/slab_check.py --n 256 --check              # parity vs numpy.fft.fftn (gathered on rank 0)
+  ... tools/slab_check.py --n 2048 --steps 5           # timing, closed-form + Parseval + round-trip checks
+
+Prints one JSON line per (size, exchange) on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, nargs="+", default=[256])
+    ap.add_argument("--exchange", nargs="+", default=["p2p", "nccl"])
+    ap.add_argument("--dtype", default="complex64")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--check", action="store_true", help="gather and compare with numpy.fft.fftn (small sizes)")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from pyfft_b200.dist import SlabPlan
+    npdt = np.dtype(args.dtype)
+    results = []
+    for n in args.n:
+        shape = (n, n, n)
+        for ex in args.exchange:
+            if world == 1 and ex != args.exchange[0]:
+                continue
+            plan = SlabPlan(shape, dtype=npdt, exchange=ex)
+            L = plan.L
+            g = torch.Generator(device=dev)
+            g.manual_seed(4242 + rank)
+            fl = torch.float32 if npdt == np.complex64 else torch.float64
+
+            def fill():
+                plan.slab.copy_(torch.view_as_complex(torch.randn(L["Zl"], n, n, 2, dtype=fl, device=dev, generator=g)))
+            rec = {"n": n, "world": world, "exchange": ex, "dtype": args.dtype}
+            fill()
+            x_local = plan.slab.clone() if (args.check or n <= 1024) else None
+            energy_in = float((plan.slab.abs() ** 2).sum().double().item())
+            plan.forward()
+            torch.cuda.synchronize()
+            energy_out = float((plan.yslab.abs() ** 2).sum().double().item())
+            if world > 1:
+                t = torch.tensor([energy_in, energy_out], dtype=torch.float64, device=dev)
+                dist.all_reduce(t)
+                energy_in, energy_out = t.tolist()
+            # Parseval: sum|X|^2 = N * sum|x|^2
+            rec["parseval_rel_err"] = abs(energy_out / (energy_in * n ** 3) - 1.0)
+            if args.check:
+                parts_x = [torch.empty_like(x_local) for _ in range(world)] if rank == 0 else None
+                parts_y = [torch.empty_like(plan.yslab) for _ in range(world)] if rank == 0 else None
+                if world > 1:
+                    dist.gather(x_local, parts_x, dst=0)
+                    dist.gather(plan.yslab.contiguous(), parts_y, dst=0)
+                else:
+                    parts_x, parts_y = [x_local], [plan.yslab]
+                if rank == 0:
+                    full = torch.cat(parts_x, dim=0).cpu().numpy()
+                    got = torch.cat(parts_y, dim=1).cpu().numpy()          # y-slabs side by side
+                    want = np.fft.fftn(full.astype(np.complex128))
+                    rec["fwd_rel_l2"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+            if x_local is not None:
+                plan.inverse()
+                torch.cuda.synchronize()
+                num = float(((plan.slab - x_local).abs() ** 2).sum().double().item())
+                den = float((x_local.abs() ** 2).sum().double().item())
+                if world > 1:
+                    t = torch.tensor([num, den], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t)
+                    num, den = t.tolist()
+                rec["roundtrip_rel_l2"] = math.sqrt(num / den)
+            # closed form: a delta at the origin transforms to all ones
+            plan.slab.zero_()
+            if rank == 0:
+                plan.slab[0, 0, 0] = 1.0
+            plan.forward()
+            torch.cuda.synchronize()
+            rec["delta_max_err"] = float((plan.yslab - 1.0).abs().max().item())
+            # timing (forward only; the graded single-exchange transform)
+            if args.steps > 0:
+                fill()
+                for _ in range(args.warmup):
+                    plan.forward()
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = plan.launch_count
+                e0.record()
+                for _ in range(args.steps):
+                    plan.forward()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / args.steps
+                if world > 1:
+                    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                N = float(n) ** 3
+                rec["ms"] = ms
+                rec["gflops"] = 5.0 * N * math.log2(N) / (ms * 1e-3) / 1e9
+                rec["launches_per_step"] = (plan.launch_count - l0) / args.steps
+                rec["sent_bytes_per_gpu"] = L["slab_elems"] * npdt.itemsize * (world - 1) / world
+                rec["nvlink_gbs_per_gpu_if_exchange_were_all"] = rec["sent_bytes_per_gpu"] / (ms * 1e-3) / 1e9
+            plan.close()
+            if rank == 0:
+                print(json.dumps(rec), flush=True)
+                results.append(rec)
+    if rank == 0 and args.out:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        json.dump(results, open(args.out, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
