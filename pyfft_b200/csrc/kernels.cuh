@@ -54,6 +54,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -71,8 +74,8 @@ struct TmaRowLayout {
     static constexpr size_t IN_BYTES = (size_t)Cfg::G * Cfg::N * 2 * sizeof(T);          // one ring slot (re+im)
     static constexpr size_t X_OFF = NBUF * IN_BYTES;
     static constexpr size_t X_BYTES = ((size_t)Cfg::SMEM_BYTES + 127) / 128 * 128;
-    static constexpr size_t BAR_OFF = X_OFF + X_BYTES;
-    static constexpr size_t TOTAL = BAR_OFF + 8 * NBUF;
+    static constexpr size_t BAR_OFF = X_OFF + X_BYTES;         // full[NBUF] then empty[NBUF]
+    static constexpr size_t TOTAL = BAR_OFF + 16 * NBUF;
 };
 
 template <class Cfg, bool SPLIT, bool INV, int MINB, int NBUF>
@@ -84,7 +87,8 @@ tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
     static_assert(Cfg::W == 1, "bulk-copy staging is for the contiguous axis");
     extern __shared__ __align__(128) unsigned char b2_smem_raw[];
     T2* xbuf = reinterpret_cast<T2*>(b2_smem_raw + L::X_OFF);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b2_smem_raw + L::BAR_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b2_smem_raw + L::BAR_OFF);      // "slot full": TMA bytes landed
+    uint64_t* empty = bars + NBUF;                                              // "slot empty": every thread has read it
     const int tid = (int)threadIdx.x;
     const long long n_groups = (p.n_tiles + Cfg::G - 1) / Cfg::G;
     const long long stride = gridDim.x;
@@ -110,7 +114,7 @@ tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < NBUF; ++b) mbar_init(&bars[b], 1);
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&bars[b], 1); mbar_init(&empty[b], Cfg::THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -126,8 +130,18 @@ tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
         mbar_wait(&bars[slot], (it / NBUF) & 1);
         const unsigned char* src = b2_smem_raw + (size_t)slot * L::IN_BYTES;
         th.load_smem(src, src + L::IN_BYTES / 2);
-        __syncthreads();                       // slot fully consumed (and the previous exchange fully read)
-        if (tid == 0) issue(grp + (long long)NBUF * stride, slot);
+        // Release the slot to the async proxy (the TMA refill).  bar.sync alone is NOT enough: it orders
+        // generic-proxy accesses only, and shared-memory loads that are still queued in the LSU were
+        // observed to read the refilled data (tools/stress_variants.py).  Each thread therefore fences its
+        // generic-proxy reads against the async proxy, then arrives on the slot's "empty" mbarrier; the
+        // elected thread waits for that phase before it issues the bulk copy.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&empty[slot]);
+        __syncthreads();                       // the previous exchange buffer contents are fully read
+        if (tid == 0 && grp + (long long)NBUF * stride < n_groups) {
+            mbar_wait(&empty[slot], (it / NBUF) & 1);
+            issue(grp + (long long)NBUF * stride, slot);
+        }
         run_stages<Cfg, SPLIT, INV, 0>(th, p, xbuf);
         th.store(p);
     }

@@ -231,3 +231,41 @@ def test_l2_chunked_schedule_is_exact(cuda_device, chunk_mb):
         assert np.array_equal(a, b)
     z = no.make_input((256, 512), 5, np.complex64, seed=11)
     assert no.rel_l2(results[1][0], no.fft_oracle(z, (256, 512), 5)) < no.tolerance(np.complex64, 256 * 512)
+
+
+def test_persistent_tma_kernels_are_race_free(cuda_device):
+    """Race detector for the persistent TMA-staged kernels: many launches over many groups per CTA must
+    be bit-identical run to run and match numpy.  (A missing generic->async proxy fence before the
+    slot refill showed up here as sporadically corrupted rows; see kernels.cuh.)"""
+    import ctypes
+    import torch
+    from pyfft_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(256)
+    stream = torch.cuda.current_stream().cuda_stream
+    checked = 0
+    for i in range(lib.b2fft_num_variants()):
+        lib.b2fft_variant_info(i, buf, len(buf))
+        f = buf.value.decode().split()
+        name, prec, lg, W, G = f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4])
+        if "_tma" not in name or lg < 9:
+            continue
+        n, rows = 1 << lg, 4096
+        cdt = np.complex64 if prec == 0 else np.complex128
+        rng = np.random.default_rng(i)
+        x = (rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))).astype(cdt)
+        a = _gpu(x, cuda_device)
+        first = None
+        for rep in range(12):
+            inplace = rep % 2 == 1
+            b = a.clone() if inplace else torch.zeros_like(a)
+            src = b if inplace else a
+            _lib.check(lib.b2fft_run_variant(i, src.data_ptr(), None, b.data_ptr(), None, 0, 0, rows, 1, 0, stream))
+            if first is None:
+                first = b
+            else:
+                assert torch.equal(first, b), (name, rep)
+        want = np.fft.fft(x.astype(np.complex128), axis=1)
+        assert no.rel_l2(first.cpu().numpy(), want) < no.tolerance(cdt, n), name
+        checked += 1
+    assert checked >= 8
