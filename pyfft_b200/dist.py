@@ -110,6 +110,12 @@ class _DeviceBuffer(object):
             self.ptr = None
 
 
+def torch_real(t):
+    """(re, im) view of a complex tensor: NCCL collectives have no complex dtypes."""
+    import torch
+    return torch.view_as_real(t).view(-1)
+
+
 def _open_peers(handles, my_rank, my_ptr, device):
     lib = _lib.load()
     ptrs = []
@@ -221,7 +227,7 @@ class SlabPlan(object):
         # X pass in place on the slab, then the Y pass whose stores are the exchange
         self._exec(self._fwd_xy, self._slab_buf.ptr, self._slab_buf.ptr, 0)
         if self.world > 1 and self.exchange == "nccl":
-            dist.all_to_all_single(self.yslab.view(-1), self._send, group=self.group)
+            dist.all_to_all_single(torch_real(self.yslab.view(-1)), torch_real(self._send), group=self.group)
         else:
             self._sync_ranks()              # all peers' blocks have landed in my y-slab
         self._exec(self._fwd_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 0)
@@ -235,7 +241,7 @@ class SlabPlan(object):
         if G > 1 and self.exchange == "nccl":
             self._exec(self._inv_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 1)
             tmp = self._send
-            dist.all_to_all_single(tmp, self.yslab.view(-1), group=self.group)
+            dist.all_to_all_single(torch_real(tmp), torch_real(self.yslab.view(-1)), group=self.group)
             # tmp = [h][Zl][Yb][X] -> slab [Zl][h*Yb + yl][X]
             self.slab.view(L["Zl"], G, L["Yb"], L["X"]).copy_(
                 tmp.view(G, L["Zl"], L["Yb"], L["X"]).permute(1, 0, 2, 3))

@@ -48,7 +48,7 @@ def test_slab_two_ranks_if_available(cuda_device):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "slab_check.py"), "--n", "64", "128",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "slab_check.py"), "--size", "64", "128",
            "--check", "--steps", "0"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]

@@ -2,8 +2,8 @@
 """Slab-decomposed 3D FFT: correctness and timing under torchrun (one rank per GPU).
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 \
-      tools/slab_check.py --n 256 --check              # parity vs numpy.fft.fftn (gathered on rank 0)
-  ... tools/slab_check.py --n 2048 --steps 5           # timing, closed-form + Parseval + round-trip checks
+      tools/slab_check.py --size 256 --check              # parity vs numpy.fft.fftn (gathered on rank 0)
+  ... tools/slab_check.py --size 2048 --steps 5           # timing, closed-form + Parseval + round-trip checks
 
 Prints one JSON line per (size, exchange) on rank 0.
 """
@@ -23,7 +23,7 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, nargs="+", default=[256])
+    ap.add_argument("--size", dest="n", type=int, nargs="+", default=[256])
     ap.add_argument("--exchange", nargs="+", default=["p2p", "nccl"])
     ap.add_argument("--dtype", default="complex64")
     ap.add_argument("--steps", type=int, default=5)
@@ -69,11 +69,15 @@ def main():
             # Parseval: sum|X|^2 = N * sum|x|^2
             rec["parseval_rel_err"] = abs(energy_out / (energy_in * n ** 3) - 1.0)
             if args.check:
-                parts_x = [torch.empty_like(x_local) for _ in range(world)] if rank == 0 else None
-                parts_y = [torch.empty_like(plan.yslab) for _ in range(world)] if rank == 0 else None
-                if world > 1:
-                    dist.gather(x_local, parts_x, dst=0)
-                    dist.gather(plan.yslab.contiguous(), parts_y, dst=0)
+                if world > 1:      # NCCL has no complex dtype: gather the (re, im) views
+                    xr, yr = torch.view_as_real(x_local).contiguous(), torch.view_as_real(plan.yslab).contiguous()
+                    px = [torch.empty_like(xr) for _ in range(world)] if rank == 0 else None
+                    py = [torch.empty_like(yr) for _ in range(world)] if rank == 0 else None
+                    dist.gather(xr, px, dst=0)
+                    dist.gather(yr, py, dst=0)
+                    if rank == 0:
+                        parts_x = [torch.view_as_complex(t) for t in px]
+                        parts_y = [torch.view_as_complex(t) for t in py]
                 else:
                     parts_x, parts_y = [x_local], [plan.yslab]
                 if rank == 0:
