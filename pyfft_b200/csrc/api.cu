@@ -52,6 +52,7 @@ int fail(int code, const char* fmt, ...) {
 struct Registry {
     std::vector<KernelVariant> v;
     std::vector<bool> prepared;
+    size_t n_default = 0;      // variants [0, n_default) are the production set, the rest tuning candidates
     std::vector<std::string> preferred;
     std::mutex mu;
     Registry() {
@@ -59,6 +60,7 @@ struct Registry {
         b2::register_f32_col(v);
         b2::register_f64_row(v);
         b2::register_f64_col(v);
+        n_default = v.size();
         b2::register_exp(v);   // tuning candidates, never picked by default (listed last)
         prepared.assign(v.size(), false);
         if (const char* e = getenv("B2FFT_PREFER")) set_preferred(e);
@@ -72,20 +74,37 @@ struct Registry {
             if (a != std::string::npos) preferred.push_back(tok.substr(a, b - a + 1));
         }
     }
-    // contiguous axis -> W == 1; strided axis -> largest-preference W dividing `inner`
+    // contiguous axis -> W == 1; strided axis -> first variant (= measured preference order) whose W
+    // divides `inner`.  Exception, measured on B200 (profiles/r01_strided_sweep.md): when consecutive
+    // rows of the transformed axis are >= 256 KiB apart (Z passes of large 3-D arrays) every row
+    // access pays a DRAM-page / TLB miss, throughput scales with the contiguous segment width, and the
+    // widest tile wins regardless of staging (W=16: 59-74 %, W=8: 37-46 %, W=4: ~20 % of peak).
     int pick(int prec, int log2n, bool contiguous, long long inner) {
         auto ok = [&](const KernelVariant& k) {
             if (k.prec != prec || k.log2n != log2n) return false;
             if (contiguous) return k.W == 1;
-            return (k.W > 1 && k.kind == 0) ? (inner % k.W == 0) : false;
+            return (k.W > 1 && k.kind != 1) ? (inner % k.W == 0) : false;
         };
         for (const auto& name : preferred)
             for (size_t i = 0; i < v.size(); ++i)
                 if (name == v[i].name && ok(v[i])) return (int)i;
+        const long long pitch = inner * (prec ? 16 : 8);
+        if (!contiguous && pitch >= (256 << 10)) {
+            int best = -1;
+            for (size_t i = 0; i < n_default; ++i)
+                if (ok(v[i]) && v[i].kind == 0 && (best < 0 || v[i].W > v[best].W)) best = (int)i;
+            if (best >= 0) return best;
+        }
         for (size_t i = 0; i < v.size(); ++i)
             if (ok(v[i])) return (int)i;
         if (!contiguous) return pick_direct_w1(prec, log2n);   // narrow inner dimension: one column per tile
         return -1;
+    }
+    // first plain strided-axis variant usable for `inner` (fallback of the tensor-map variants)
+    int pick_direct_col(int prec, int log2n, long long inner) {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].prec == prec && v[i].log2n == log2n && v[i].W > 1 && v[i].kind == 0 && inner % v[i].W == 0) return (int)i;
+        return pick_direct_w1(prec, log2n);
     }
     // first plain (non-TMA) W = 1 variant: strided fallback, and the fallback for unaligned pointers
     int pick_direct_w1(int prec, int log2n) {
@@ -207,7 +226,7 @@ int build_passes(b2fft_plan* pl) {
         const KernelVariant& kv = reg.v[vi];
         Pass p{};
         p.variant = vi;
-        p.fallback = kv.kind == 0 ? vi : reg.pick_direct_w1(pl->prec, lg);
+        p.fallback = kv.kind == 0 ? vi : kv.kind == 1 ? reg.pick_direct_w1(pl->prec, lg) : reg.pick_direct_col(pl->prec, lg, inner[a]);
         if (p.fallback < 0) return fail(B2FFT_E_UNSUPPORTED, "no fallback kernel for axis %c", "xyz"[a]);
         p.axis = a;
         p.log2n = lg;
@@ -245,8 +264,11 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
                 long long outer_count, bool last, cudaStream_t stream) {
     const bool split = pl->layout == B2FFT_SPLIT;
     int vi = ps.variant;
-    if (registry().v[vi].kind == 1) {   // TMA bulk copies need 16-byte aligned sources
-        if (((uintptr_t)in0 % 16) != 0 || (split && ((uintptr_t)in1 % 16) != 0)) vi = ps.fallback;
+    if (registry().v[vi].kind != 0) {   // TMA needs 16-byte aligned sources (and 16-byte multiples as row pitch)
+        const size_t pitch = (size_t)ps.inner * (split ? sizeof(T) : 2 * sizeof(T));
+        if (((uintptr_t)in0 % 16) != 0 || (split && ((uintptr_t)in1 % 16) != 0) ||
+            (registry().v[vi].kind == 2 && (pitch % 16 != 0 || outer_count > 0x7fffffffLL)))
+            vi = ps.fallback;
     }
     const KernelVariant& kv = registry().v[vi];
     b2::PassParams<T> p{};

@@ -1,6 +1,7 @@
 // __global__ wrappers around the tile thread program + the variant registry.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -71,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <class Cfg, int NBUF>
 struct TmaRowLayout {
     using T = typename Cfg::T;
-    static constexpr size_t IN_BYTES = (size_t)Cfg::G * Cfg::N * 2 * sizeof(T);          // one ring slot (re+im)
+    static constexpr size_t IN_BYTES = (size_t)Cfg::G * Cfg::N * Cfg::W * 2 * sizeof(T);  // one ring slot (re+im)
     static constexpr size_t X_OFF = NBUF * IN_BYTES;
     static constexpr size_t X_BYTES = ((size_t)Cfg::SMEM_BYTES + 127) / 128 * 128;
     static constexpr size_t BAR_OFF = X_OFF + X_BYTES;         // full[NBUF] then empty[NBUF]
@@ -147,6 +148,97 @@ tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
     }
 }
 
+// ------------------------------------------------------------------ persistent TMA-staged kernel (strided axes)
+// Same pipeline as the row version, for tiles of W columns of an [outer][N][inner] array: the tile is
+// fetched with cp.async.bulk.tensor (TMA tiled loads, SASS UTMALDG) through a 3-D tensor map
+// {inner, N, outer} in boxes of {W, NB, 1}; the boxes land densely as [N][W], which is exactly the
+// layout TileThread::load_smem() reads.  Address generation for the strided gather is done by the TMA
+// unit and the next tile is in flight while the current one is in registers.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <class Cfg>
+struct TmaColBox {
+    static constexpr int NB = Cfg::N < 256 ? Cfg::N : 256;     // rows per TMA box (box dims are <= 256)
+    static constexpr int NLOAD = Cfg::N / NB;
+};
+
+template <class Cfg, bool SPLIT, bool INV, int MINB, int NBUF, bool BLK>
+__global__ void __launch_bounds__(Cfg::THREADS, MINB)
+tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, const __grid_constant__ CUtensorMap tm0,
+                        const __grid_constant__ CUtensorMap tm1) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    using L = TmaRowLayout<Cfg, NBUF>;                 // same ring / exchange / barrier layout (IN_BYTES = G*N*W complex)
+    constexpr int NB = TmaColBox<Cfg>::NB, NLOAD = TmaColBox<Cfg>::NLOAD;
+    extern __shared__ __align__(128) unsigned char b2_smem_raw[];
+    T2* xbuf = reinterpret_cast<T2*>(b2_smem_raw + L::X_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b2_smem_raw + L::BAR_OFF);
+    uint64_t* empty = bars + NBUF;
+    const int tid = (int)threadIdx.x;
+    const long long n_groups = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    const long long stride = gridDim.x;
+
+    auto issue = [&](long long grp, int slot) {
+        if (grp >= n_groups) return;
+        long long tiles = p.n_tiles - grp * Cfg::G;
+        if (tiles > Cfg::G) tiles = Cfg::G;
+        unsigned char* dst = b2_smem_raw + (size_t)slot * L::IN_BYTES;
+        constexpr uint32_t plane_bytes = (uint32_t)(Cfg::N * Cfg::W * sizeof(T));      // one tile, one real plane
+        mbar_expect_tx(&bars[slot], (uint32_t)tiles * 2u * plane_bytes);
+        for (int g = 0; g < (int)tiles; ++g) {
+            const long long tile = grp * Cfg::G + g;
+            const long long o = tile / p.inner_blocks, ib = tile - o * p.inner_blocks;
+#pragma unroll
+            for (int nb = 0; nb < NLOAD; ++nb) {
+                if constexpr (SPLIT) {
+                    unsigned char* d0 = dst + ((size_t)g * Cfg::N + (size_t)nb * NB) * Cfg::W * sizeof(T);
+                    tma_load_3d(d0, &tm0, (int)(ib * Cfg::W), nb * NB, (int)o, &bars[slot]);
+                    tma_load_3d(d0 + L::IN_BYTES / 2, &tm1, (int)(ib * Cfg::W), nb * NB, (int)o, &bars[slot]);
+                } else {
+                    unsigned char* d0 = dst + ((size_t)g * Cfg::N + (size_t)nb * NB) * Cfg::W * 2 * sizeof(T);
+                    tma_load_3d(d0, &tm0, (int)(ib * Cfg::W * 2), nb * NB, (int)o, &bars[slot]);
+                }
+            }
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&bars[b], 1); mbar_init(&empty[b], Cfg::THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long grp = blockIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) issue(grp + b * stride, b);
+    }
+    TileThread<Cfg, SPLIT, INV> th;
+    for (unsigned it = 0; grp < n_groups; ++it, grp += stride) {
+        const int slot = (int)(it % NBUF);
+        th.setup(tid, grp, p);
+        mbar_wait(&bars[slot], (it / NBUF) & 1);
+        const unsigned char* src = b2_smem_raw + (size_t)slot * L::IN_BYTES;
+        th.load_smem(src, src + L::IN_BYTES / 2);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // see tile_fft_kernel_tma_row
+        mbar_arrive(&empty[slot]);
+        __syncthreads();
+        if (tid == 0 && grp + (long long)NBUF * stride < n_groups) {
+            mbar_wait(&empty[slot], (it / NBUF) & 1);
+            issue(grp + (long long)NBUF * stride, slot);
+        }
+        run_stages<Cfg, SPLIT, INV, 0>(th, p, xbuf);
+        th.template store<BLK>(p);
+    }
+    if constexpr (BLK) __threadfence_system();
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -157,7 +249,7 @@ struct KernelVariant {
     int threads;
     long long smem_bytes;
     int minb;
-    int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis only)
+    int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis), 2 = persistent + TMA tensor staging (strided axes)
     int nbuf;        // ring depth for kind 1
     int blk;         // 1: also compiled with destination-blocked stores (slab exchange passes)
     // launches ceil(n_tiles / G) CTAs; params points at a PassParams<T> of the right T
@@ -296,6 +388,114 @@ struct VariantOpsTma {
     }
 };
 
+// ---- host side of the tensor-map variants
+typedef CUresult (*b2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline b2_encode_tiled_fn b2_get_encode_tiled() {
+    static b2_encode_tiled_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (b2_encode_tiled_fn)f;
+    }();
+    return fn;
+}
+
+// {inner (x elems_per_complex), N, outer} view of one plane pointer, boxes {W (x epc), NB, 1}
+template <typename T>
+inline cudaError_t b2_make_col_map(CUtensorMap* tm, const void* base, int epc, long long inner, int N, long long outer,
+                                   int W, int NB) {
+    b2_encode_tiled_fn enc = b2_get_encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = {(cuuint64_t)(inner * epc), (cuuint64_t)N, (cuuint64_t)outer};
+    const cuuint64_t strides[2] = {(cuuint64_t)(inner * epc) * sizeof(T), (cuuint64_t)(inner * epc) * N * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)(W * epc), (cuuint32_t)NB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <class Cfg, int MINB, int NBUF>
+struct VariantOpsTmaCol {
+    using T = typename Cfg::T;
+    using L = TmaRowLayout<Cfg, NBUF>;
+    static int& slots() { static int s = 0; return s; }
+    template <bool SPLIT, bool INV, bool BLK>
+    static cudaError_t attr() {
+        return cudaFuncSetAttribute(tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, BLK>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+    }
+    static cudaError_t prepare() {
+        cudaError_t e;
+        if ((e = attr<false, false, false>()) != cudaSuccess) return e;
+        if ((e = attr<false, true, false>()) != cudaSuccess) return e;
+        if ((e = attr<true, false, false>()) != cudaSuccess) return e;
+        if ((e = attr<false, false, true>()) != cudaSuccess) return e;
+        if ((e = attr<false, true, true>()) != cudaSuccess) return e;
+        if ((e = attr<true, false, true>()) != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_fft_kernel_tma_col<Cfg, false, false, MINB, NBUF, false>,
+                                                          Cfg::THREADS, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return b2_get_encode_tiled() ? cudaSuccess : cudaErrorNotSupported;
+    }
+    template <bool SPLIT, bool INV>
+    static void go(bool blk, dim3 grid, dim3 block, size_t sm, cudaStream_t st, const PassParams<T>& p, const CUtensorMap& a,
+                   const CUtensorMap& b) {
+        if (blk) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, true><<<grid, block, sm, st>>>(p, a, b);
+        else tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false><<<grid, block, sm, st>>>(p, a, b);
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+        if (ctas <= 0) return cudaSuccess;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        if (ctas > slots()) ctas = slots();
+        const long long outer = p.n_tiles / p.inner_blocks;
+        constexpr int NB = TmaColBox<Cfg>::NB;
+        alignas(64) CUtensorMap tm0, tm1;
+        cudaError_t e = b2_make_col_map<T>(&tm0, p.in0, split ? 1 : 2, p.inner, Cfg::N, outer, Cfg::W, NB);
+        if (e != cudaSuccess) return e;
+        tm1 = tm0;
+        if (split) {
+            e = b2_make_col_map<T>(&tm1, p.in1, 1, p.inner, Cfg::N, outer, Cfg::W, NB);
+            if (e != cudaSuccess) return e;
+        }
+        const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
+        const bool blk = p.out_blk_log2 >= 0;
+        if (split) go<true, false>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
+        else if (inv) go<false, true>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
+        else go<false, false>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_fft_kernel_tma_col<Cfg, false, false, MINB, NBUF, false>,
+                                                          Cfg::THREADS, L::TOTAL) != cudaSuccess)
+            return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v = VariantOps<Cfg, MINB, false>::make(name);
+        v.smem_bytes = (long long)L::TOTAL;
+        v.kind = 2;
+        v.nbuf = NBUF;
+        v.blk = 1;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        return v;
+    }
+};
+
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x
 #define B2_STR(x) B2_STR2(x)
@@ -312,6 +512,11 @@ struct VariantOpsTma {
 #define B2_VT(T, L, G, MB, NB, R0, R1, R2, R3)                                                       \
     out.push_back(::b2::VariantOpsTma<::b2::TileCfg<T, L, 1, G, R0, R1, R2, R3>, MB, NB>::make(        \
         #T "_n" B2_STR(L) "_w1_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tma" B2_STR(NB)));
+
+// B2_VC(type, log2n, W, G, minblocks, ring depth, R0..R3): persistent TMA tensor-staged strided-axis variant
+#define B2_VC(T, L, W, G, MB, NB, R0, R1, R2, R3)                                                    \
+    out.push_back(::b2::VariantOpsTmaCol<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, NB>::make(     \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmac" B2_STR(NB)));
 
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);

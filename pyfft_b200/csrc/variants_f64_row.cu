@@ -6,8 +6,10 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #define B2_GROUP_F64_ROW
 #define X B2_V
 #define XT B2_VT
+#define XC B2_VC
 #include "variants.def"
 #undef X
 #undef XT
+#undef XC
 }
 }  // namespace b2

@@ -79,6 +79,10 @@ def slab_layout(shape, world_size, rank):
         # inverse: Z pass of rank h writes z-block g to  slab_g + inv_peer_offset, z planes Y*X apart
         "inv_peer_offset": rank * Yb * X,
         "inv_out_inner": Y * X, "inv_out_outer_stride": 0,
+        # "yzx" y-slab layout [Yb][Z][X]: the Z pass then strides by X only (a Y-pass-like access pattern)
+        # instead of Yb*X; the Y pass's stores stride by Z*X between consecutive y instead of X.
+        "fwd_peer_offset_yzx": rank * Zl * X, "fwd_out_inner_yzx": Z * X, "fwd_out_outer_stride_yzx": X,
+        "inv_out_outer_stride_yzx": X,
     }
 
 
@@ -138,13 +142,18 @@ class SlabPlan(object):
     """
 
     def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
-                 exchange="p2p", device=None):
+                 exchange="p2p", device=None, yslab_layout="zyx"):
         import torch
         import torch.distributed as dist
         if len(shape) != 3:
             raise ValueError("SlabPlan needs a 3D shape (Z, Y, X)")
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if yslab_layout not in ("zyx", "yzx"):
+            raise ValueError("yslab_layout must be 'zyx' ([Z][Yb][X]) or 'yzx' ([Yb][Z][X])")
+        if yslab_layout == "yzx" and exchange != "p2p":
+            raise ValueError("the 'yzx' y-slab layout needs the fused p2p exchange")
+        self.yslab_layout = yslab_layout
         self._torch, self._dist = torch, dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -170,14 +179,19 @@ class SlabPlan(object):
 
         X, Y, Z, Zl, Yb = L["X"], L["Y"], L["Z"], L["Zl"], L["Yb"]
         self._fwd_xy = make((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 0)     # forward: scale applied by the Z pass
-        self._fwd_z = make((X, Yb, Z), _lib.AXIS_Z, 1)
-        self._inv_z = make((X, Yb, Z), _lib.AXIS_Z, 0)                    # inverse: scale applied by the X/Y passes
+        yzx = yslab_layout == "yzx"
+        if yzx:      # y-slab stored [Yb][Z][X]: the z axis is the middle ("y") axis of that array
+            self._fwd_z = make((X, Z, Yb), _lib.AXIS_Y, 1)
+            self._inv_z = make((X, Z, Yb), _lib.AXIS_Y, 0)
+        else:
+            self._fwd_z = make((X, Yb, Z), _lib.AXIS_Z, 1)
+            self._inv_z = make((X, Yb, Z), _lib.AXIS_Z, 0)                # inverse: scale applied by the X/Y passes
         self._inv_xy = make((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 1)
 
         self._slab_buf = _DeviceBuffer(L["slab_elems"] * self.esz, self.device)
         self._yslab_buf = _DeviceBuffer(L["yslab_elems"] * self.esz, self.device)
         self.slab = self._slab_buf.tensor(self.tdtype).view(Zl, Y, X)
-        self.yslab = self._yslab_buf.tensor(self.tdtype).view(Z, Yb, X)
+        self.yslab = self._yslab_buf.tensor(self.tdtype).view(*((Yb, Z, X) if yzx else (Z, Yb, X)))
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
         self._send = None
 
@@ -187,18 +201,20 @@ class SlabPlan(object):
             dist.all_gather_object(hs, (self._slab_buf.handle(), self._yslab_buf.handle()), group=group)
             self._peer_slab = _open_peers([h[0] for h in hs], self.rank, self._slab_buf.ptr, self.device)
             self._peer_yslab = _open_peers([h[1] for h in hs], self.rank, self._yslab_buf.ptr, self.device)
-            fwd_ptrs = [p + L["fwd_peer_offset"] * self.esz for p in self._peer_yslab]
+            sfx = "_yzx" if yzx else ""
+            fwd_ptrs = [p + L["fwd_peer_offset" + sfx] * self.esz for p in self._peer_yslab]
             inv_ptrs = [p + L["inv_peer_offset"] * self.esz for p in self._peer_slab]
-            self._set_blocks(self._fwd_xy, fwd_ptrs, L["fwd_out_inner"], L["fwd_out_outer_stride"])
-            self._set_blocks(self._inv_z, inv_ptrs, L["inv_out_inner"], L["inv_out_outer_stride"])
+            self._set_blocks(self._fwd_xy, fwd_ptrs, L["fwd_out_inner" + sfx], L["fwd_out_outer_stride" + sfx])
+            self._set_blocks(self._inv_z, inv_ptrs, L["inv_out_inner"], L["inv_out_outer_stride" + sfx])
         elif G > 1:
             self._send = torch.empty(L["slab_elems"], dtype=self.tdtype, device="cuda:%d" % self.device)
             fwd_ptrs = [self._send.data_ptr() + h * L["block_elems"] * self.esz for h in range(G)]
             self._set_blocks(self._fwd_xy, fwd_ptrs, L["fwd_out_inner"], L["fwd_out_outer_stride"])
         else:
             # single rank: the "exchange" is the Y pass writing into the y-slab buffer directly
-            self._set_blocks(self._fwd_xy, [self._yslab_buf.ptr], L["fwd_out_inner"], L["fwd_out_outer_stride"])
-            self._set_blocks(self._inv_z, [self._slab_buf.ptr], L["inv_out_inner"], L["inv_out_outer_stride"])
+            sfx = "_yzx" if yzx else ""
+            self._set_blocks(self._fwd_xy, [self._yslab_buf.ptr], L["fwd_out_inner" + sfx], L["fwd_out_outer_stride" + sfx])
+            self._set_blocks(self._inv_z, [self._slab_buf.ptr], L["inv_out_inner"], L["inv_out_outer_stride" + sfx])
 
     # ------------------------------------------------------------------ helpers
     def _set_blocks(self, plan, ptrs, out_inner, out_outer_stride):

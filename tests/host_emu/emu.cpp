@@ -92,8 +92,14 @@ static double run_case(long long outer, long long inner, unsigned seed, bool sta
         if (staged) {
             long long tiles = p.n_tiles - bid * Cfg::G;
             if (tiles > Cfg::G) tiles = Cfg::G;
-            const long long first = bid * Cfg::G * N, cnt = tiles * N;     // W == 1, inner == 1
-            for (long long i = 0; i < cnt; ++i) { st_c[i] = in_c[first + i]; st_re[i] = in_re[first + i]; st_im[i] = in_im[first + i]; }
+            for (long long g = 0; g < tiles; ++g) {                          // dense [g][n][w] staging, as TMA delivers it
+                const long long tile = bid * Cfg::G + g, o = tile / p.inner_blocks, ib = tile % p.inner_blocks;
+                for (int n = 0; n < N; ++n)
+                    for (int w = 0; w < Cfg::W; ++w) {
+                        const long long src = (o * N + n) * inner + ib * Cfg::W + w, dst = (g * N + n) * Cfg::W + w;
+                        st_c[dst] = in_c[src]; st_re[dst] = in_re[src]; st_im[dst] = in_im[src];
+                    }
+            }
         }
         for (int tid = 0; tid < Cfg::THREADS; ++tid) {
             th[tid].setup(tid, bid, p);
@@ -205,9 +211,10 @@ template <class Cfg>
 static void check_staged(const char* name, long long outer) {
     using T = typename Cfg::T;
     const double tol = sizeof(T) == 4 ? 3e-6 : 1e-14;
-    double e0 = run_case<Cfg, false, false>(outer, 1, 4, true);
-    double e1 = run_case<Cfg, false, true>(outer, 1, 5, true);
-    double e2 = run_case<Cfg, true, false>(outer, 1, 6, true);
+    const long long inner = Cfg::W == 1 ? 1 : 3 * Cfg::W;
+    double e0 = run_case<Cfg, false, false>(outer, inner, 4, true);
+    double e1 = run_case<Cfg, false, true>(outer, inner, 5, true);
+    double e2 = run_case<Cfg, true, false>(outer, inner, 6, true);
     bool ok = e0 < tol && e1 < tol && e2 < tol;
     std::printf("%-44s outer=%lld staged   err fwd=%.2e inv=%.2e split=%.2e %s\n", name, outer, e0, e1, e2, ok ? "ok" : "FAIL");
     if (!ok) ++g_fail;
@@ -215,6 +222,9 @@ static void check_staged(const char* name, long long outer) {
 
 #define CHKT(T, L, G, R0, R1, R2, R3) \
     check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
+
+#define CHKC(T, L, W, G, R0, R1, R2, R3) \
+    check_staged<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tmac", 3);
 
 #define CHK(T, L, W, G, R0, R1, R2, R3, OUTER, INNER) \
     check<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER); \

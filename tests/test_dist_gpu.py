@@ -15,18 +15,22 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("layout", ["zyx", "yzx"])
 @pytest.mark.parametrize("shape,dtype", [((32, 64, 128), np.complex64), ((64, 32, 16), np.complex128), ((256, 256, 256), np.complex64)])
-def test_slab_plan_single_rank(cuda_device, shape, dtype):
+def test_slab_plan_single_rank(cuda_device, shape, dtype, layout):
     import torch
     from pyfft_b200.dist import SlabPlan
-    plan = SlabPlan(shape, dtype=dtype)
+    plan = SlabPlan(shape, dtype=dtype, yslab_layout=layout)
     x = no.make_input(shape, 1, dtype, seed=9)[0]
     plan.slab.copy_(torch.from_numpy(x).to(cuda_device))
     y = plan.forward()
     torch.cuda.synchronize()
     want = np.fft.fftn(x.astype(np.complex128))
     tol = no.tolerance(dtype, int(np.prod(shape)))
-    assert no.rel_l2(y.cpu().numpy(), want) < tol
+    got = y.cpu().numpy()
+    if layout == "yzx":
+        got = got.transpose(1, 0, 2)
+    assert no.rel_l2(got, want) < tol
     back = plan.inverse()
     torch.cuda.synchronize()
     assert no.rel_l2(back.cpu().numpy(), x) < tol
@@ -49,10 +53,10 @@ def test_slab_two_ranks_if_available(cuda_device):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "slab_check.py"), "--size", "64", "128",
-           "--check", "--steps", "0"]
+           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     recs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
-    assert len(recs) == 4
+    assert len(recs) == 6
     for r in recs:
         assert r["fwd_rel_l2"] < 1e-5 * 21 and r["roundtrip_rel_l2"] < 1e-5 * 21 and r["delta_max_err"] < 1e-4, r

@@ -234,9 +234,9 @@ def test_l2_chunked_schedule_is_exact(cuda_device, chunk_mb):
 
 
 def test_persistent_tma_kernels_are_race_free(cuda_device):
-    """Race detector for the persistent TMA-staged kernels: many launches over many groups per CTA must
-    be bit-identical run to run and match numpy.  (A missing generic->async proxy fence before the
-    slot refill showed up here as sporadically corrupted rows; see kernels.cuh.)"""
+    """Race detector for the persistent TMA-staged kernels (row and strided): many launches over many
+    groups per CTA must be bit-identical run to run and match numpy.  (A missing generic->async proxy
+    fence before the slot refill showed up here as sporadically corrupted rows; see kernels.cuh.)"""
     import ctypes
     import torch
     from pyfft_b200 import _lib
@@ -248,19 +248,22 @@ def test_persistent_tma_kernels_are_race_free(cuda_device):
         lib.b2fft_variant_info(i, buf, len(buf))
         f = buf.value.decode().split()
         name, prec, lg, W, G = f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4])
-        if "_tma" not in name or lg < 9:
+        if "_tma" not in name or lg < 8:
             continue
-        n, rows = 1 << lg, 4096
+        n = 1 << lg
+        inner = 1 if W == 1 else 512
+        outer = 4096 if W == 1 else max(2, 4096 * 1024 // (n * inner))
         cdt = np.complex64 if prec == 0 else np.complex128
         rng = np.random.default_rng(i)
-        x = (rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))).astype(cdt)
+        x = (rng.standard_normal((outer, n, inner)) + 1j * rng.standard_normal((outer, n, inner))).astype(cdt)
         a = _gpu(x, cuda_device)
+        n_tiles = outer * (inner // W)
         first = None
         for rep in range(12):
             inplace = rep % 2 == 1
             b = a.clone() if inplace else torch.zeros_like(a)
             src = b if inplace else a
-            _lib.check(lib.b2fft_run_variant(i, src.data_ptr(), None, b.data_ptr(), None, 0, 0, rows, 1, 0, stream))
+            _lib.check(lib.b2fft_run_variant(i, src.data_ptr(), None, b.data_ptr(), None, 0, 0, n_tiles, inner, 0, stream))
             if first is None:
                 first = b
             else:
@@ -268,4 +271,4 @@ def test_persistent_tma_kernels_are_race_free(cuda_device):
         want = np.fft.fft(x.astype(np.complex128), axis=1)
         assert no.rel_l2(first.cpu().numpy(), want) < no.tolerance(cdt, n), name
         checked += 1
-    assert checked >= 8
+    assert checked >= 12

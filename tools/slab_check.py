@@ -24,7 +24,7 @@ import torch.distributed as dist  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", dest="n", type=int, nargs="+", default=[256])
-    ap.add_argument("--exchange", nargs="+", default=["p2p", "nccl"])
+    ap.add_argument("--exchange", nargs="+", default=["p2p", "nccl"], help="p2p | nccl | p2p-yzx ([Yb][Z][X] y-slab layout)")
     ap.add_argument("--dtype", default="complex64")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
@@ -47,7 +47,8 @@ def main():
         for ex in args.exchange:
             if world == 1 and ex != args.exchange[0]:
                 continue
-            plan = SlabPlan(shape, dtype=npdt, exchange=ex)
+            yzx = ex.endswith("-yzx")
+            plan = SlabPlan(shape, dtype=npdt, exchange=ex.split("-")[0], yslab_layout="yzx" if yzx else "zyx")
             L = plan.L
             g = torch.Generator(device=dev)
             g.manual_seed(4242 + rank)
@@ -82,7 +83,10 @@ def main():
                     parts_x, parts_y = [x_local], [plan.yslab]
                 if rank == 0:
                     full = torch.cat(parts_x, dim=0).cpu().numpy()
-                    got = torch.cat(parts_y, dim=1).cpu().numpy()          # y-slabs side by side
+                    if yzx:
+                        got = torch.cat([t.permute(1, 0, 2) for t in parts_y], dim=1).cpu().numpy()
+                    else:
+                        got = torch.cat(parts_y, dim=1).cpu().numpy()      # y-slabs side by side
                     want = np.fft.fftn(full.astype(np.complex128))
                     rec["fwd_rel_l2"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
             if x_local is not None:

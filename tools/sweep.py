@@ -63,6 +63,8 @@ def main():
         n = 1 << lg
         csize = 8 if prec == 0 else 16
         inner = 1 if W == 1 else max(W, args.inner)
+        if W > 1 and n * inner * csize > nbytes:
+            continue
         n_el = nbytes // csize
         lines = n_el // n                     # number of columns
         if W > 1:
