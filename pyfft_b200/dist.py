@@ -142,7 +142,7 @@ class SlabPlan(object):
     """
 
     def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
-                 exchange="p2p", device=None, yslab_layout="zyx"):
+                 exchange="p2p", device=None, yslab_layout="zyx", chunks=1):
         import torch
         import torch.distributed as dist
         if len(shape) != 3:
@@ -154,6 +154,9 @@ class SlabPlan(object):
         if yslab_layout == "yzx" and exchange != "p2p":
             raise ValueError("the 'yzx' y-slab layout needs the fused p2p exchange")
         self.yslab_layout = yslab_layout
+        # exchange="nccl" only: the slab is processed in `chunks` groups of z planes; the all-to-all of
+        # chunk c runs on a side stream while the X/Y passes of chunk c+1 compute
+        self.chunks = max(1, int(chunks))
         self._torch, self._dist = torch, dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -208,8 +211,23 @@ class SlabPlan(object):
             self._set_blocks(self._inv_z, inv_ptrs, L["inv_out_inner"], L["inv_out_outer_stride" + sfx])
         elif G > 1:
             self._send = torch.empty(L["slab_elems"], dtype=self.tdtype, device="cuda:%d" % self.device)
-            fwd_ptrs = [self._send.data_ptr() + h * L["block_elems"] * self.esz for h in range(G)]
-            self._set_blocks(self._fwd_xy, fwd_ptrs, L["fwd_out_inner"], L["fwd_out_outer_stride"])
+            C = self.chunks
+            while Zl % C:
+                C -= 1
+            self.chunks = C
+            Zc = Zl // C
+            cb = Zc * Yb * X                                  # elements one rank receives from me per chunk
+            self._chunk_plans = []
+            for c in range(C):
+                pl = make((X, Y, Zc), _lib.AXIS_X | _lib.AXIS_Y, 0)
+                ptrs = [self._send.data_ptr() + (c * G + h) * cb * self.esz for h in range(G)]
+                self._set_blocks(pl, ptrs, L["fwd_out_inner"], L["fwd_out_outer_stride"])
+                self._chunk_plans.append(pl)
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+            sendr = torch.view_as_real(self._send).view(C, G, cb * 2)
+            recvr = torch.view_as_real(self.yslab.view(-1)).view(G, C, cb * 2)   # z = (g, c, z') -> natural z order
+            self._send_lists = [[sendr[c, h] for h in range(G)] for c in range(C)]
+            self._recv_lists = [[recvr[g, c] for g in range(G)] for c in range(C)]
         else:
             # single rank: the "exchange" is the Y pass writing into the y-slab buffer directly
             sfx = "_yzx" if yzx else ""
@@ -233,18 +251,34 @@ class SlabPlan(object):
 
     @property
     def launch_count(self):
-        return sum(int(self._lib.b2fft_plan_launch_count(p)) for p in (self._fwd_xy, self._fwd_z, self._inv_z, self._inv_xy))
+        plans = [self._fwd_xy, self._fwd_z, self._inv_z, self._inv_xy] + list(getattr(self, "_chunk_plans", []))
+        return sum(int(self._lib.b2fft_plan_launch_count(p)) for p in plans if p is not None)
 
     # ------------------------------------------------------------------ transforms
     def forward(self):
         """``plan.slab`` (destroyed) -> ``plan.yslab``.  Asynchronous on the current stream."""
         L, dist = self.L, self._dist
         self._sync_ranks()                  # every rank is done with its previous y-slab contents
-        # X pass in place on the slab, then the Y pass whose stores are the exchange
-        self._exec(self._fwd_xy, self._slab_buf.ptr, self._slab_buf.ptr, 0)
         if self.world > 1 and self.exchange == "nccl":
-            dist.all_to_all_single(torch_real(self.yslab.view(-1)), torch_real(self._send), group=self.group)
+            # per z-chunk: X pass in place, Y pass with destination-blocked stores into the send buffer,
+            # then that chunk's all-to-all on the side stream while the next chunk computes
+            torch = self._torch
+            cur = torch.cuda.current_stream(self.device)
+            chunk_bytes = (L["slab_elems"] // self.chunks) * self.esz
+            works = []
+            for c, pl in enumerate(self._chunk_plans):
+                ptr = self._slab_buf.ptr + c * chunk_bytes
+                self._exec(pl, ptr, ptr, 0)
+                self._comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self._comm_stream):
+                    works.append(dist.all_to_all(self._recv_lists[c], self._send_lists[c], group=self.group,
+                                                 async_op=True))
+            for w in works:
+                w.wait()                    # current stream waits for the exchange
+            cur.wait_stream(self._comm_stream)
         else:
+            # X pass in place on the slab, then the Y pass whose stores are the exchange
+            self._exec(self._fwd_xy, self._slab_buf.ptr, self._slab_buf.ptr, 0)
             self._sync_ranks()              # all peers' blocks have landed in my y-slab
         self._exec(self._fwd_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 0)
         return self.yslab
@@ -273,6 +307,10 @@ class SlabPlan(object):
             if h is not None:
                 self._lib.b2fft_plan_destroy(h)
                 setattr(self, p, None)
+        for h in getattr(self, "_chunk_plans", []):
+            self._lib.b2fft_plan_destroy(h)
+        self._chunk_plans = []
+        self._send_lists = self._recv_lists = None
         self.slab = self.yslab = None
         if getattr(self, "_peer_slab", None):
             for r, p in enumerate(self._peer_slab):

@@ -53,10 +53,10 @@ def test_slab_two_ranks_if_available(cuda_device):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "slab_check.py"), "--size", "64", "128",
-           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx"]
+           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx", "ncclx4"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     recs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
-    assert len(recs) == 6
+    assert len(recs) == 8
     for r in recs:
         assert r["fwd_rel_l2"] < 1e-5 * 21 and r["roundtrip_rel_l2"] < 1e-5 * 21 and r["delta_max_err"] < 1e-4, r

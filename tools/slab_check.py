@@ -48,7 +48,9 @@ def main():
             if world == 1 and ex != args.exchange[0]:
                 continue
             yzx = ex.endswith("-yzx")
-            plan = SlabPlan(shape, dtype=npdt, exchange=ex.split("-")[0], yslab_layout="yzx" if yzx else "zyx")
+            chunks = int(ex.split("x")[1]) if ex.startswith("ncclx") else 1          # "ncclx8" = 8 pipelined chunks
+            plan = SlabPlan(shape, dtype=npdt, exchange="nccl" if ex.startswith("nccl") else ex.split("-")[0],
+                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks)
             L = plan.L
             g = torch.Generator(device=dev)
             g.manual_seed(4242 + rank)
