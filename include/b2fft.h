@@ -75,8 +75,15 @@ B2FFT_API int b2fft_plan_create_ex(b2fft_plan** out, const int64_t dims_xyz[3], 
                          int apply_scale);
 
 /* Replaces the temp-buffer sizing of FFTPlan._execute (pyfft/plan.py:184-192).  The caller
- * (Python: torch caching allocator or the user's mempool) owns the workspace. */
+ * (Python: torch caching allocator or the user's mempool) owns the workspace.  Plans whose axes all
+ * fit one CTA (x <= 2^14 single / 2^13 double, y and z <= 2^11) need none.  Longer axes are split
+ * four-step style into a transposing pass + the rest (the counterpart of the reference's
+ * global-kernel chains, pyfft/plan.py:141-143); such plans need one data-sized buffer for in-place
+ * executes (b2fft_plan_workspace_bytes) and, only when the long axis is not the first pass, for
+ * out-of-place executes too (b2fft_plan_workspace_bytes_ex with in_place = 0).  The workspace must
+ * be 16-byte aligned and stay valid until the execute has finished on its stream. */
 B2FFT_API int b2fft_plan_workspace_bytes(const b2fft_plan* plan, int64_t batch, size_t* out);
+B2FFT_API int b2fft_plan_workspace_bytes_ex(const b2fft_plan* plan, int64_t batch, int in_place, size_t* out);
 B2FFT_API int b2fft_plan_set_workspace(b2fft_plan* plan, void* dptr, size_t bytes);
 
 /* Replaces FFTPlan._execute + Function.__call__ (pyfft/plan.py:173-259, pyfft/cuda.py:35-46).

@@ -27,6 +27,7 @@ SIGNATURES = {
     "b2fft_plan_create": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_i64), _i, _i, _i, _d, _i, _i]),
     "b2fft_plan_create_ex": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _i, _i, _i, _d, _i, _i, _d, _i]),
     "b2fft_plan_workspace_bytes": (_i, [_vp, _i64, ctypes.POINTER(_sz)]),
+    "b2fft_plan_workspace_bytes_ex": (_i, [_vp, _i64, _i, ctypes.POINTER(_sz)]),
     "b2fft_plan_set_workspace": (_i, [_vp, _vp, _sz]),
     "b2fft_execute": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "b2fft_plan_destroy": (_i, [_vp]),

@@ -101,10 +101,38 @@ struct Registry {
         return -1;
     }
     // first plain strided-axis variant usable for `inner` (fallback of the tensor-map variants)
-    int pick_direct_col(int prec, int log2n, long long inner) {
+    int pick_direct_col(int prec, int log2n, long long inner, bool need_fs = false) {
         for (size_t i = 0; i < v.size(); ++i)
-            if (v[i].prec == prec && v[i].log2n == log2n && v[i].W > 1 && v[i].kind == 0 && inner % v[i].W == 0) return (int)i;
-        return pick_direct_w1(prec, log2n);
+            if (v[i].prec == prec && v[i].log2n == log2n && v[i].W > 1 && v[i].kind == 0 && inner % v[i].W == 0 &&
+                (!need_fs || v[i].fs))
+                return (int)i;
+        return need_fs ? -1 : pick_direct_w1(prec, log2n);
+    }
+    // four-step "A" pass: first FS-capable strided-axis variant whose W divides `inner`
+    int pick_fs(int prec, int log2n, long long inner) {
+        auto ok = [&](const KernelVariant& k) {
+            return k.prec == prec && k.log2n == log2n && k.fs && k.W > 1 && inner % k.W == 0;
+        };
+        for (const auto& name : preferred)
+            for (size_t i = 0; i < v.size(); ++i)
+                if (name == v[i].name && ok(v[i])) return (int)i;
+        const long long pitch = inner * (prec ? 16 : 8);
+        if (pitch >= (256 << 10)) {   // see pick(): very long row pitch -> widest plain tile
+            int best = -1;
+            for (size_t i = 0; i < n_default; ++i)
+                if (ok(v[i]) && v[i].kind == 0 && (best < 0 || v[i].W > v[best].W)) best = (int)i;
+            if (best >= 0) return best;
+        }
+        for (size_t i = 0; i < v.size(); ++i)
+            if (ok(v[i])) return (int)i;
+        return -1;
+    }
+    // longest transform a single pass can do (contiguous axis: W == 1 variants, strided: W > 1)
+    int max_log2(int prec, bool contiguous) {
+        int m = 0;
+        for (size_t i = 0; i < n_default; ++i)
+            if (v[i].prec == prec && (contiguous ? v[i].W == 1 : v[i].W > 1) && v[i].log2n > m) m = v[i].log2n;
+        return m;
     }
     // first plain (non-TMA) W = 1 variant: strided fallback, and the fallback for unaligned pointers
     int pick_direct_w1(int prec, int log2n) {
@@ -150,6 +178,40 @@ struct TwiddleCache {
         return 0;
     }
 };
+// four-step inter-pass twiddle tables (see PassParams::fs_t1 / fs_t2 in fft_core.cuh)
+struct FsTwiddleCache {
+    std::mutex mu;
+    std::map<std::tuple<int, int, int, long long, long long, int>, void*> tabs;   // (device, prec, which, N, N2, rows)
+    template <typename T>
+    int make(long long N, long long N2, int rows, long long mult, void** out) {
+        const auto h = b2::make_fs_table<T>(N, N2, rows, mult);
+        void* d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(h[0])));
+        CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice));
+        *out = d;
+        return 0;
+    }
+    // which = 1: [TPC][N2] w_N^(t*n2);  which = 2: [E][N2] w_N^(TPC*c*n2)
+    int get(int device, int prec, int which, long long N, long long N2, int TPC, int E, const void** out) {
+        std::lock_guard<std::mutex> lk(mu);
+        const int rows = which == 1 ? TPC : E;
+        auto key = std::make_tuple(device, prec, which, N, N2, rows);
+        auto it = tabs.find(key);
+        if (it != tabs.end()) { *out = it->second; return 0; }
+        void* d = nullptr;
+        const long long mult = which == 1 ? 1 : TPC;
+        int rc = prec == B2FFT_F32 ? make<float>(N, N2, rows, mult, &d) : make<double>(N, N2, rows, mult, &d);
+        if (rc) return rc;
+        tabs[key] = d;
+        *out = d;
+        return 0;
+    }
+};
+FsTwiddleCache& fs_twiddles() {
+    static FsTwiddleCache c;
+    return c;
+}
+
 TwiddleCache& twiddles() {
     static TwiddleCache c;
     return c;
@@ -185,9 +247,14 @@ struct Pass {
     int log2n;
     long long n;
     long long inner;       // element stride of the transformed axis
-    long long outer;       // lines groups per transform: number of [n][inner] blocks per single transform
     const void* tw[3];
     const void* tw_fb[3];  // twiddle tables of the fallback variant (its radices may differ)
+    // four-step "A" pass (transposing): this pass is the length-n = N1 part of an axis of length
+    // fs_total = N1*N2 whose elements are inner0 apart; it stores [n2][k1][inner0]
+    bool transposing;
+    long long fs_total, fs_n2, inner0;
+    const void* fs_t1; const void* fs_t2;        // tables for `variant`
+    const void* fs_t1_fb; const void* fs_t2_fb;  // ... and for `fallback`
 };
 
 }  // namespace
@@ -207,55 +274,100 @@ struct b2fft_plan {
     void* blk1[B2_MAX_BLOCKS] = {};
     long long blk_out_inner = 0, blk_out_outer_stride = 0;
     std::atomic<long long> launches{0};
+    int n_transposing = 0;   // four-step "A" passes (cannot run in place)
 };
 
 namespace {
 
-int build_passes(b2fft_plan* pl) {
+int stage_tables(b2fft_plan* pl, const KernelVariant& kv, long long n, const void** tw) {
+    int NS = (int)n;
+    for (int s = 0; s + 1 < kv.S; ++s) {
+        int rc = twiddles().get(pl->device, pl->prec, NS, kv.radix[s], &tw[s]);
+        if (rc) return rc;
+        NS /= kv.radix[s];
+    }
+    return 0;
+}
+
+// One kernel pass over [..][n][inner]; fs_total > 0 makes it the transposing first part of a
+// four-step decomposition of an axis of length fs_total = n * N2 (inner = N2 * inner0).
+int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contiguous, long long fs_total, long long inner0) {
     Registry& reg = registry();
+    const int lg = ilog2ll(n);
+    const bool fs = fs_total > 0;
+    int vi = fs ? reg.pick_fs(pl->prec, lg, inner) : reg.pick(pl->prec, lg, contiguous, inner);
+    if (vi < 0)
+        return fail(B2FFT_E_UNSUPPORTED, "no kernel for axis %c of length %lld (%s) in this build", "xyz"[axis], n,
+                    pl->prec ? "f64" : "f32");
+    const KernelVariant& kv = reg.v[vi];
+    Pass p{};
+    p.variant = vi;
+    p.fallback = kv.kind == 0 ? vi : kv.kind == 1 ? reg.pick_direct_w1(pl->prec, lg) : reg.pick_direct_col(pl->prec, lg, inner, fs);
+    if (p.fallback < 0) return fail(B2FFT_E_UNSUPPORTED, "no fallback kernel for axis %c", "xyz"[axis]);
+    p.axis = axis;
+    p.log2n = lg;
+    p.n = n;
+    p.inner = inner;
+    int rc = stage_tables(pl, kv, n, p.tw);
+    if (rc) return rc;
+    cudaError_t e = reg.prepare(vi);
+    if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+    const KernelVariant& fb = reg.v[p.fallback];
+    if (p.fallback != vi) {
+        rc = stage_tables(pl, fb, n, p.tw_fb);
+        if (rc) return rc;
+        e = reg.prepare(p.fallback);
+        if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+    } else {
+        for (int s = 0; s < 3; ++s) p.tw_fb[s] = p.tw[s];
+    }
+    if (fs) {
+        p.transposing = true;
+        p.fs_total = fs_total;
+        p.fs_n2 = fs_total / n;
+        p.inner0 = inner0;
+        for (int which = 1; which <= 2; ++which) {
+            rc = fs_twiddles().get(pl->device, pl->prec, which, fs_total, p.fs_n2, (int)(n / kv.E), kv.E,
+                                   which == 1 ? &p.fs_t1 : &p.fs_t2);
+            if (rc) return rc;
+            rc = fs_twiddles().get(pl->device, pl->prec, which, fs_total, p.fs_n2, (int)(n / fb.E), fb.E,
+                                   which == 1 ? &p.fs_t1_fb : &p.fs_t2_fb);
+            if (rc) return rc;
+        }
+    }
+    pl->passes.push_back(p);
+    return 0;
+}
+
+// All passes of one axis of length n whose elements are `inner` apart.  Lengths beyond what one
+// CTA can hold are split four-step style, n = N1*N2: a transposing pass over n1 (stride N2*inner)
+// with the inter-pass twiddle fused into its stores, then (recursively) the axis of length N2 with
+// element stride N1*inner.  This replaces the reference's global-kernel chains
+// (pyfft/plan.py:141-143, pyfft/kernel.py:259-283) with 2 (n <= 2^22) or 3 DRAM round trips.
+int add_axis(b2fft_plan* pl, int axis, long long n, long long inner, bool contiguous) {
+    Registry& reg = registry();
+    const int lg = ilog2ll(n);
+    if (lg <= reg.max_log2(pl->prec, contiguous)) return add_pass(pl, axis, n, inner, contiguous, 0, 0);
+    const int col = reg.max_log2(pl->prec, false);
+    if (col < 1) return fail(B2FFT_E_UNSUPPORTED, "no strided-axis kernels in this build");
+    const int npass = (lg + col - 1) / col;
+    const int l1 = lg / npass;
+    const long long n1 = 1LL << l1, n2 = n >> l1;
+    int rc = add_pass(pl, axis, n1, n2 * inner, false, n, inner);
+    if (rc) return rc;
+    return add_axis(pl, axis, n2, n1 * inner, false);
+}
+
+int build_passes(b2fft_plan* pl) {
     const long long dims[3] = {pl->x, pl->y, pl->z};
     const long long inner[3] = {1, pl->x, pl->x * pl->y};
-    const long long outer[3] = {pl->y * pl->z, pl->z, 1};
     for (int a = 0; a < 3; ++a) {
         if (!(pl->axes_mask & (1 << a)) || dims[a] <= 1) continue;
-        const int lg = ilog2ll(dims[a]);
-        int vi = reg.pick(pl->prec, lg, a == 0, inner[a]);
-        if (vi < 0)
-            return fail(B2FFT_E_UNSUPPORTED, "no kernel for axis %c of length %lld (%s) in this build", "xyz"[a],
-                        dims[a], pl->prec ? "f64" : "f32");
-        const KernelVariant& kv = reg.v[vi];
-        Pass p{};
-        p.variant = vi;
-        p.fallback = kv.kind == 0 ? vi : kv.kind == 1 ? reg.pick_direct_w1(pl->prec, lg) : reg.pick_direct_col(pl->prec, lg, inner[a]);
-        if (p.fallback < 0) return fail(B2FFT_E_UNSUPPORTED, "no fallback kernel for axis %c", "xyz"[a]);
-        p.axis = a;
-        p.log2n = lg;
-        p.n = dims[a];
-        p.inner = inner[a];
-        p.outer = outer[a];
-        int NS = (int)dims[a];
-        for (int s = 0; s + 1 < kv.S; ++s) {
-            int rc = twiddles().get(pl->device, pl->prec, NS, kv.radix[s], &p.tw[s]);
-            if (rc) return rc;
-            NS /= kv.radix[s];
-        }
-        cudaError_t e = reg.prepare(vi);
-        if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
-        if (p.fallback != vi) {
-            const KernelVariant& fb = reg.v[p.fallback];
-            NS = (int)dims[a];
-            for (int s = 0; s + 1 < fb.S; ++s) {
-                int rc = twiddles().get(pl->device, pl->prec, NS, fb.radix[s], &p.tw_fb[s]);
-                if (rc) return rc;
-                NS /= fb.radix[s];
-            }
-            e = reg.prepare(p.fallback);
-            if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
-        } else {
-            for (int s = 0; s < 3; ++s) p.tw_fb[s] = p.tw[s];
-        }
-        pl->passes.push_back(p);
+        int rc = add_axis(pl, a, dims[a], inner[a], a == 0);
+        if (rc) return rc;
     }
+    pl->n_transposing = 0;
+    for (const Pass& p : pl->passes) pl->n_transposing += p.transposing ? 1 : 0;
     return 0;
 }
 
@@ -285,6 +397,14 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
     p.out_inner = p.inner;
     p.out_outer_stride = p.outer_stride;
     p.out_blk_log2 = -1;
+    if (ps.transposing) {
+        p.out_inner = ps.inner0;
+        p.fs_log2_inner = ilog2ll(ps.inner0);
+        p.fs_n2 = ps.fs_n2;
+        p.fs_col_stride = ps.n * ps.inner0;
+        p.fs_t1 = (const T*)(vi == ps.variant ? ps.fs_t1 : ps.fs_t1_fb);
+        p.fs_t2 = (const T*)(vi == ps.variant ? ps.fs_t2 : ps.fs_t2_fb);
+    }
     if (last && pl->nblocks > 0) {
         if (!kv.blk) return fail(B2FFT_E_UNSUPPORTED, "kernel %s has no destination-blocked store", kv.name);
         if (ps.n % pl->nblocks) return fail(B2FFT_E_INVALID, "last axis length %lld not divisible into %d blocks", ps.n, pl->nblocks);
@@ -358,9 +478,28 @@ int b2fft_plan_create(b2fft_plan** out, int rank, const int64_t dims_xyz[3], int
                                 scale, fast_math, device, 0.0, 1);
 }
 
+// Single-pass-per-axis plans work tile-in-place and need no scratch memory.  Plans with four-step
+// (transposing) passes need one buffer of the size of the data when the transposing pass cannot
+// write straight into `out`: always for in-place executes, and for out-of-place executes when a
+// transposing pass is not the first pass.
+static size_t workspace_need(const b2fft_plan* plan, int64_t batch, bool in_place) {
+    if (plan->n_transposing == 0) return 0;
+    int later = 0;
+    for (size_t i = 1; i < plan->passes.size(); ++i) later += plan->passes[i].transposing ? 1 : 0;
+    if (!in_place && later == 0) return 0;
+    const size_t csize = plan->prec ? 16 : 8;
+    return (size_t)(plan->x * plan->y * plan->z) * (size_t)batch * csize;
+}
+
 int b2fft_plan_workspace_bytes(const b2fft_plan* plan, int64_t batch, size_t* out) {
     if (!plan || !out || batch < 0) return fail(B2FFT_E_INVALID, "bad argument");
-    *out = 0;   // every pass works tile-in-place; no pass needs scratch memory
+    *out = workspace_need(plan, batch, true);
+    return B2FFT_OK;
+}
+
+int b2fft_plan_workspace_bytes_ex(const b2fft_plan* plan, int64_t batch, int in_place, size_t* out) {
+    if (!plan || !out || batch < 0) return fail(B2FFT_E_INVALID, "bad argument");
+    *out = workspace_need(plan, batch, in_place != 0);
     return B2FFT_OK;
 }
 
@@ -394,6 +533,49 @@ int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0
             const size_t bytes = (size_t)(plan->x * plan->y * plan->z) * (size_t)batch * esz;
             CUDA_TRY(cudaMemcpyAsync(out0, in0, bytes, cudaMemcpyDeviceToDevice, stream));
             if (split) CUDA_TRY(cudaMemcpyAsync(out1, in1, bytes, cudaMemcpyDeviceToDevice, stream));
+        }
+        return B2FFT_OK;
+    }
+    const size_t np_all = plan->passes.size();
+    if (plan->n_transposing > 0) {
+        // ---- four-step plans: a transposing pass must write to a different buffer than it reads.
+        // Walk backwards from "result in out": a transposing pass reads the other buffer of
+        // {out, workspace}, any other pass runs in place.  The first pass of an out-of-place execute
+        // reads `in` whatever it writes; an in-place execute that would have to start in the
+        // workspace lets its last (never transposing) pass move the data instead.
+        const bool in_place = (in0 == out0) || (split && in1 == out1);
+        const size_t need = workspace_need(plan, batch, in_place);
+        if (need > plan->workspace_bytes || (need && !plan->workspace))
+            return fail(B2FFT_E_INVALID, "this plan needs a workspace of %zu bytes for batch %lld (have %zu); see "
+                        "b2fft_plan_workspace_bytes_ex / b2fft_plan_set_workspace", need, (long long)batch, plan->workspace_bytes);
+        if (need && ((uintptr_t)plan->workspace % 16) != 0) return fail(B2FFT_E_INVALID, "workspace must be 16-byte aligned");
+        enum { OUT = 1, WS = 2 };
+        int src[16], dst[16];
+        if (np_all > 16) return fail(B2FFT_E_UNSUPPORTED, "too many passes");
+        int loc = OUT;
+        for (size_t k = np_all; k-- > 0;) {
+            dst[k] = loc;
+            const bool move = plan->passes[k].transposing ||
+                              (in_place && k + 1 == np_all && (plan->n_transposing & 1));
+            src[k] = move ? (loc == OUT ? WS : OUT) : loc;
+            loc = src[k];
+        }
+        const size_t plane = (size_t)(plan->x * plan->y * plan->z) * (size_t)batch * (plan->prec ? 8 : 4);
+        void* ws0 = plan->workspace;
+        void* ws1 = split ? (void*)((char*)plan->workspace + plane) : nullptr;
+        const long long vol = plan->x * plan->y * plan->z;
+        for (size_t k = 0; k < np_all; ++k) {
+            const Pass& ps = plan->passes[k];
+            const void* ci0 = (k == 0) ? in0 : (src[k] == OUT ? out0 : ws0);
+            const void* ci1 = (k == 0) ? in1 : (src[k] == OUT ? out1 : ws1);
+            void* co0 = dst[k] == OUT ? out0 : ws0;
+            void* co1 = dst[k] == OUT ? out1 : ws1;
+            const long long blocks = batch * (vol / (ps.n * ps.inner));
+            const bool last = k + 1 == np_all;
+            int rc = plan->prec == B2FFT_F32
+                         ? launch_pass<float>(plan, ps, ci0, ci1, co0, co1, inverse, blocks, last, stream)
+                         : launch_pass<double>(plan, ps, ci0, ci1, co0, co1, inverse, blocks, last, stream);
+            if (rc) return rc;
         }
         return B2FFT_OK;
     }
@@ -533,8 +715,12 @@ int b2fft_plan_describe(const b2fft_plan* plan, char* buf, size_t buflen) {
     std::string s;
     for (const Pass& p : plan->passes) {
         char line[256];
-        snprintf(line, sizeof line, "axis=%c n=%lld inner=%lld variant=%s\n", "XYZ"[p.axis], p.n, p.inner,
-                 registry().v[p.variant].name);
+        if (p.transposing)
+            snprintf(line, sizeof line, "axis=%c n=%lld inner=%lld variant=%s fs=%lldx%lld\n", "XYZ"[p.axis], p.n, p.inner,
+                     registry().v[p.variant].name, p.n, p.fs_n2);
+        else
+            snprintf(line, sizeof line, "axis=%c n=%lld inner=%lld variant=%s\n", "XYZ"[p.axis], p.n, p.inner,
+                     registry().v[p.variant].name);
         s += line;
     }
     snprintf(buf, buflen, "%s", s.c_str());
@@ -580,10 +766,10 @@ int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, v
     if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
     const long long inner_blocks = inner / k.W;
     if (n_tiles % inner_blocks != 0) return fail(B2FFT_E_INVALID, "n_tiles must be a multiple of inner/W");
-    p.outer = n_tiles / inner_blocks;
+    const long long outer = n_tiles / inner_blocks;
     return k.prec == B2FFT_F32
-               ? launch_pass<float>(&tmp, p, in0, in1, out0, out1, inverse, p.outer, false, (cudaStream_t)cuda_stream)
-               : launch_pass<double>(&tmp, p, in0, in1, out0, out1, inverse, p.outer, false, (cudaStream_t)cuda_stream);
+               ? launch_pass<float>(&tmp, p, in0, in1, out0, out1, inverse, outer, false, (cudaStream_t)cuda_stream)
+               : launch_pass<double>(&tmp, p, in0, in1, out0, out1, inverse, outer, false, (cudaStream_t)cuda_stream);
 }
 
 int b2fft_set_option(const char* key, double value) {

@@ -133,6 +133,16 @@ struct PassParams {
     int out_blk_log2;        // < 0: plain stores to out0/out1
     T* out_blk0[B2_MAX_BLOCKS];
     T* out_blk1[B2_MAX_BLOCKS];
+    // four-step "A" pass (FS kernels only): the transformed axis of length N = N1*N2 is split as
+    // n = n1*N2 + n2; this pass transforms over n1 (length Cfg::N = N1, element stride N2*inner0,
+    // so the pass's `inner` is N2*inner0), multiplies output k1 of column n2 by w_N^(k1*n2) and
+    // stores it TRANSPOSED at [outer][n2][k1][inner0] (out_inner = inner0).  The following pass
+    // over n2 (element stride N1*inner0) then leaves X[k1 + N1*k2] in natural order.
+    int fs_log2_inner;        // log2(inner0)
+    long long fs_n2;          // N2
+    long long fs_col_stride;  // N1 * inner0: output element stride between consecutive n2
+    const T* fs_t1;           // vec2<T> [TPC][N2]: w_N^(t*n2)
+    const T* fs_t2;           // vec2<T> [E][N2]:   w_N^(TPC*c*n2)
 };
 
 // ------------------------------------------------------------------ compile-time plan
@@ -207,7 +217,7 @@ B2_HD T ld_stream1(const T* p) {
 }
 
 // ------------------------------------------------------------------ the thread program
-template <class Cfg, bool SPLIT, bool INV>
+template <class Cfg, bool SPLIT, bool INV, bool FS = false>
 struct TileThread {
     using T = typename Cfg::T;
     using T2 = vec2<T>;
@@ -218,6 +228,7 @@ struct TileThread {
     bool active;
     long long base;       // element offset of (n = 0, this column) in the input
     long long obase;      // ... and in the output
+    long long fs_n2i;     // FS: this column's n2
 
     B2_HD void setup(int tid, long long bid, const PassParams<T>& p) {
         w = tid % W;
@@ -229,7 +240,14 @@ struct TileThread {
         if (p.inner_blocks > 1) { o = tile / p.inner_blocks; ib = tile - o * p.inner_blocks; }
         else { o = tile; ib = 0; }
         base = o * p.outer_stride + ib * W + w;
-        obase = o * p.out_outer_stride + ib * W + w;
+        if constexpr (FS) {
+            const long long c = ib * W + w;                       // column inside [N2][inner0]
+            fs_n2i = c >> p.fs_log2_inner;
+            obase = o * p.out_outer_stride + fs_n2i * p.fs_col_stride + (c - (fs_n2i << p.fs_log2_inner));
+        } else {
+            fs_n2i = 0;
+            obase = o * p.out_outer_stride + ib * W + w;
+        }
     }
 
     // ---- stage 0 input: element n = t + TPC*j  (BPT(0) == 1)
@@ -355,6 +373,29 @@ struct TileThread {
         if (!active) return;
         constexpr int s = S - 1;
         constexpr int R = Cfg::R(s), LG = ilog2(R), BPT = Cfg::BPT(s);
+        if constexpr (FS) {
+            // inter-pass twiddle w_N^(k1*n2), k1 = t + TPC*c, as the product of two table entries
+            const T2* t1p = reinterpret_cast<const T2*>(p.fs_t1) + (long long)t * p.fs_n2 + fs_n2i;
+            const T2* t2p = reinterpret_cast<const T2*>(p.fs_t2) + fs_n2i;
+            const T2 b = *t1p;
+            static_for<0, BPT>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                static_for<0, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int q = i * R + brev(k, LG);
+                    constexpr int c = i + k * BPT;
+                    T wr = b.x, wi = b.y;
+                    if constexpr (c > 0) {
+                        const T2 sv = t2p[(long long)c * p.fs_n2];
+                        wr = b.x * sv.x - b.y * sv.y;
+                        wi = b.x * sv.y + b.y * sv.x;
+                    }
+                    const T xr = re[q], xi = im[q];
+                    re[q] = xr * wr - xi * wi;
+                    im[q] = xr * wi + xi * wr;
+                });
+            });
+        }
         if (p.scale_mode == 1) {
             static_for<0, E>([&](auto jc) { re[decltype(jc)::value] *= p.scale; im[decltype(jc)::value] *= p.scale; });
         } else if (p.scale_mode == 2) {

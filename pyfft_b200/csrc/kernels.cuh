@@ -10,8 +10,8 @@
 
 namespace b2 {
 
-template <class Cfg, bool SPLIT, bool INV, int s>
-__device__ __forceinline__ void run_stages(TileThread<Cfg, SPLIT, INV>& th, const PassParams<typename Cfg::T>& p,
+template <class Cfg, bool SPLIT, bool INV, int s, class TH>
+__device__ __forceinline__ void run_stages(TH& th, const PassParams<typename Cfg::T>& p,
                                            vec2<typename Cfg::T>* smem) {
     th.template compute<s>(p);
     if constexpr (s + 1 < Cfg::S) {
@@ -23,12 +23,15 @@ __device__ __forceinline__ void run_stages(TileThread<Cfg, SPLIT, INV>& th, cons
     }
 }
 
-template <class Cfg, bool SPLIT, bool INV, int MINB, bool BLK = false>
+// BLK: destination-blocked stores (slab exchange); FS: four-step "A" pass (transposed store +
+// inter-pass twiddle, see PassParams).  The two are never combined.
+template <class Cfg, bool SPLIT, bool INV, int MINB, bool BLK = false, bool FS = false>
 __global__ void __launch_bounds__(Cfg::THREADS, MINB)
 tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
+    static_assert(!(BLK && FS), "blocked and transposed stores are exclusive");
     extern __shared__ __align__(16) unsigned char b2_smem_raw[];
     auto* smem = reinterpret_cast<vec2<typename Cfg::T>*>(b2_smem_raw);
-    TileThread<Cfg, SPLIT, INV> th;
+    TileThread<Cfg, SPLIT, INV, FS> th;
     th.setup((int)threadIdx.x, (long long)blockIdx.x, p);
     th.load(p);
     run_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
@@ -168,7 +171,7 @@ struct TmaColBox {
     static constexpr int NLOAD = Cfg::N / NB;
 };
 
-template <class Cfg, bool SPLIT, bool INV, int MINB, int NBUF, bool BLK>
+template <class Cfg, bool SPLIT, bool INV, int MINB, int NBUF, bool BLK, bool FS = false>
 __global__ void __launch_bounds__(Cfg::THREADS, MINB)
 tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, const __grid_constant__ CUtensorMap tm0,
                         const __grid_constant__ CUtensorMap tm1) {
@@ -219,7 +222,7 @@ tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, c
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) issue(grp + b * stride, b);
     }
-    TileThread<Cfg, SPLIT, INV> th;
+    TileThread<Cfg, SPLIT, INV, FS> th;
     for (unsigned it = 0; grp < n_groups; ++it, grp += stride) {
         const int slot = (int)(it % NBUF);
         th.setup(tid, grp, p);
@@ -252,6 +255,7 @@ struct KernelVariant {
     int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis), 2 = persistent + TMA tensor staging (strided axes)
     int nbuf;        // ring depth for kind 1
     int blk;         // 1: also compiled with destination-blocked stores (slab exchange passes)
+    int fs;          // 1: also compiled as a four-step "A" pass (transposed store + inter-pass twiddle)
     // launches ceil(n_tiles / G) CTAs; params points at a PassParams<T> of the right T
     cudaError_t (*launch)(int split, int inv, const void* params, cudaStream_t stream);
     cudaError_t (*prepare)();   // one-time function attributes (dynamic smem opt-in)
@@ -259,28 +263,35 @@ struct KernelVariant {
     int (*occupancy)();
 };
 
-template <class Cfg, int MINB, bool BLKCAP = false>
+template <class Cfg, int MINB, bool BLKCAP = false, bool FSCAP = false>
 struct VariantOps {
     using T = typename Cfg::T;
+    template <bool SPLIT, bool INV, bool BLK, bool FS>
+    static cudaError_t attr() {
+        return cudaFuncSetAttribute(tile_fft_kernel<Cfg, SPLIT, INV, MINB, BLK, FS>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    }
+    template <bool BLK, bool FS>
+    static cudaError_t attr3() {
+        cudaError_t e;
+        if ((e = attr<false, false, BLK, FS>()) != cudaSuccess) return e;
+        if ((e = attr<false, true, BLK, FS>()) != cudaSuccess) return e;
+        return attr<true, false, BLK, FS>();
+    }
     static cudaError_t prepare() {
         cudaError_t e = cudaSuccess;
         if (Cfg::SMEM_BYTES > 48 * 1024) {
-            const int b = (int)Cfg::SMEM_BYTES;
-            if constexpr (BLKCAP) {
-                e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, false, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-                if (e != cudaSuccess) return e;
-                e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, true, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-                if (e != cudaSuccess) return e;
-                e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, true, false, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-                if (e != cudaSuccess) return e;
-            }
-            e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, false, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(tile_fft_kernel<Cfg, true, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+            if constexpr (BLKCAP) { if ((e = attr3<true, false>()) != cudaSuccess) return e; }
+            if constexpr (FSCAP) { if ((e = attr3<false, true>()) != cudaSuccess) return e; }
+            e = attr3<false, false>();
         }
         return e;
+    }
+    template <bool BLK, bool FS>
+    static void go(int split, int inv, dim3 grid, dim3 block, size_t sm, cudaStream_t stream, const PassParams<T>& p) {
+        if (split) tile_fft_kernel<Cfg, true, false, MINB, BLK, FS><<<grid, block, sm, stream>>>(p);
+        else if (inv) tile_fft_kernel<Cfg, false, true, MINB, BLK, FS><<<grid, block, sm, stream>>>(p);
+        else tile_fft_kernel<Cfg, false, false, MINB, BLK, FS><<<grid, block, sm, stream>>>(p);
     }
     static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
         const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
@@ -290,18 +301,14 @@ struct VariantOps {
         const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
         const size_t sm = (size_t)Cfg::SMEM_BYTES;
         if (p.out_blk_log2 >= 0) {
-            if constexpr (BLKCAP) {
-                if (split) tile_fft_kernel<Cfg, true, false, MINB, true><<<grid, block, sm, stream>>>(p);
-                else if (inv) tile_fft_kernel<Cfg, false, true, MINB, true><<<grid, block, sm, stream>>>(p);
-                else tile_fft_kernel<Cfg, false, false, MINB, true><<<grid, block, sm, stream>>>(p);
-                return cudaGetLastError();
-            } else {
-                return cudaErrorNotSupported;
-            }
+            if constexpr (BLKCAP) go<true, false>(split, inv, grid, block, sm, stream, p);
+            else return cudaErrorNotSupported;
+        } else if (p.fs_t1 != nullptr) {
+            if constexpr (FSCAP) go<false, true>(split, inv, grid, block, sm, stream, p);
+            else return cudaErrorNotSupported;
+        } else {
+            go<false, false>(split, inv, grid, block, sm, stream, p);
         }
-        if (split) tile_fft_kernel<Cfg, true, false, MINB><<<grid, block, sm, stream>>>(p);
-        else if (inv) tile_fft_kernel<Cfg, false, true, MINB><<<grid, block, sm, stream>>>(p);
-        else tile_fft_kernel<Cfg, false, false, MINB><<<grid, block, sm, stream>>>(p);
         return cudaGetLastError();
     }
     static int occupancy() {
@@ -322,6 +329,7 @@ struct VariantOps {
         v.smem_bytes = Cfg::SMEM_BYTES;
         v.minb = MINB;
         v.blk = BLKCAP ? 1 : 0;
+        v.fs = FSCAP ? 1 : 0;
         v.launch = &launch;
         v.prepare = &prepare;
         v.occupancy = &occupancy;
@@ -420,14 +428,14 @@ inline cudaError_t b2_make_col_map(CUtensorMap* tm, const void* base, int epc, l
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <class Cfg, int MINB, int NBUF>
+template <class Cfg, int MINB, int NBUF, bool FSCAP = false>
 struct VariantOpsTmaCol {
     using T = typename Cfg::T;
     using L = TmaRowLayout<Cfg, NBUF>;
     static int& slots() { static int s = 0; return s; }
-    template <bool SPLIT, bool INV, bool BLK>
+    template <bool SPLIT, bool INV, bool BLK, bool FS = false>
     static cudaError_t attr() {
-        return cudaFuncSetAttribute(tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, BLK>,
+        return cudaFuncSetAttribute(tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, BLK, FS>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
     }
     static cudaError_t prepare() {
@@ -438,6 +446,11 @@ struct VariantOpsTmaCol {
         if ((e = attr<false, false, true>()) != cudaSuccess) return e;
         if ((e = attr<false, true, true>()) != cudaSuccess) return e;
         if ((e = attr<true, false, true>()) != cudaSuccess) return e;
+        if constexpr (FSCAP) {
+            if ((e = attr<false, false, false, true>()) != cudaSuccess) return e;
+            if ((e = attr<false, true, false, true>()) != cudaSuccess) return e;
+            if ((e = attr<true, false, false, true>()) != cudaSuccess) return e;
+        }
         int dev = 0, sms = 0, occ = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -451,7 +464,9 @@ struct VariantOpsTmaCol {
     static void go(bool blk, dim3 grid, dim3 block, size_t sm, cudaStream_t st, const PassParams<T>& p, const CUtensorMap& a,
                    const CUtensorMap& b) {
         if (blk) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, true><<<grid, block, sm, st>>>(p, a, b);
-        else tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false><<<grid, block, sm, st>>>(p, a, b);
+        else if (p.fs_t1 != nullptr) {
+            if constexpr (FSCAP) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false, true><<<grid, block, sm, st>>>(p, a, b);
+        } else tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false><<<grid, block, sm, st>>>(p, a, b);
     }
     static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
         const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
@@ -471,6 +486,7 @@ struct VariantOpsTmaCol {
         }
         const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
         const bool blk = p.out_blk_log2 >= 0;
+        if (!FSCAP && p.fs_t1 != nullptr) return cudaErrorNotSupported;
         if (split) go<true, false>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
         else if (inv) go<false, true>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
         else go<false, false>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
@@ -489,6 +505,7 @@ struct VariantOpsTmaCol {
         v.kind = 2;
         v.nbuf = NBUF;
         v.blk = 1;
+        v.fs = FSCAP ? 1 : 0;
         v.launch = &launch;
         v.prepare = &prepare;
         v.occupancy = &occupancy;
@@ -508,6 +525,11 @@ struct VariantOpsTmaCol {
     out.push_back(::b2::VariantOps<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, true>::make(         \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3)));
 
+// B2_VF: like B2_VB, additionally compiled as a four-step "A" pass (transposed store + twiddle)
+#define B2_VF(T, L, W, G, MB, R0, R1, R2, R3)                                                        \
+    out.push_back(::b2::VariantOps<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, true, true>::make(   \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3)));
+
 // B2_VT(type, log2n, G, minblocks, ring depth, R0, R1, R2, R3): persistent TMA-staged contiguous-axis variant
 #define B2_VT(T, L, G, MB, NB, R0, R1, R2, R3)                                                       \
     out.push_back(::b2::VariantOpsTma<::b2::TileCfg<T, L, 1, G, R0, R1, R2, R3>, MB, NB>::make(        \
@@ -516,6 +538,11 @@ struct VariantOpsTmaCol {
 // B2_VC(type, log2n, W, G, minblocks, ring depth, R0..R3): persistent TMA tensor-staged strided-axis variant
 #define B2_VC(T, L, W, G, MB, NB, R0, R1, R2, R3)                                                    \
     out.push_back(::b2::VariantOpsTmaCol<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, NB>::make(     \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmac" B2_STR(NB)));
+
+// B2_VCF: like B2_VC, additionally compiled as a four-step "A" pass
+#define B2_VCF(T, L, W, G, MB, NB, R0, R1, R2, R3)                                                   \
+    out.push_back(::b2::VariantOpsTmaCol<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, NB, true>::make( \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmac" B2_STR(NB)));
 
 void register_f32_row(std::vector<KernelVariant>& out);

@@ -60,4 +60,20 @@ std::vector<vec2<T>> make_stage_table(int NS, int R) {
     return tab;
 }
 
+// Four-step inter-pass twiddle tables (PassParams::fs_t1 / fs_t2):
+//   tab[r*N2 + n2] = exp(-2*pi*i * mult*r*n2 / N),  r = 0..rows-1, n2 = 0..N2-1
+// fs_t1: rows = TPC, mult = 1;  fs_t2: rows = E, mult = TPC.
+template <typename T>
+std::vector<vec2<T>> make_fs_table(long long N, long long N2, int rows, long long mult) {
+    std::vector<vec2<T>> tab((size_t)rows * (size_t)N2);
+    for (int r = 0; r < rows; ++r)
+        for (long long n2 = 0; n2 < N2; ++n2) {
+            long double c, s;
+            unit_root((mult * r * n2) % N, N, c, s);
+            tab[(size_t)r * N2 + n2].x = (T)c;
+            tab[(size_t)r * N2 + n2].y = (T)s;
+        }
+    return tab;
+}
+
 }  // namespace b2

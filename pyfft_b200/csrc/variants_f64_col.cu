@@ -7,9 +7,13 @@ void register_f64_col(std::vector<KernelVariant>& out) {
 #define X B2_VB
 #define XT B2_VT
 #define XC B2_VC
+#define XF B2_VF
+#define XCF B2_VCF
 #include "variants.def"
 #undef X
 #undef XT
 #undef XC
+#undef XF
+#undef XCF
 }
 }  // namespace b2

@@ -135,7 +135,8 @@ class FFTPlan(object):
         self._wait_for_finish = wait_for_finish
         self._itemsize = self._dtype.itemsize
         self._workspace = None
-        self._last_batch_size = 0
+        self._workspace_bytes = 0
+        self._last_batch_size = None
 
         self._lib = _lib.load()                # raises if the CUDA library is not built
         self._device = context.device_index()
@@ -187,18 +188,23 @@ class FFTPlan(object):
                 raise TypeError("%s has dtype %s, the plan was created for %s" % (what, tdtype, self._dtype))
         return ptr
 
-    def _ensure_workspace(self, batch):
+    def _ensure_workspace(self, batch, in_place):
         """Workspace is owned by the caller side of the C ABI (plan.py:184-192 re-allocates the
-        reference's temp buffer per batch size the same way)."""
-        if batch == self._last_batch_size:
+        reference's temp buffer per batch size the same way).  Only plans with an axis too long
+        for one pass need one, and out-of-place executes of a long first axis do not."""
+        key = (batch, bool(in_place))
+        if key == self._last_batch_size:
             return
         need = ctypes.c_size_t(0)
-        _lib.check(self._lib.b2fft_plan_workspace_bytes(self._handle, batch, ctypes.byref(need)))
-        if need.value:
+        _lib.check(self._lib.b2fft_plan_workspace_bytes_ex(self._handle, batch, int(bool(in_place)),
+                                                           ctypes.byref(need)))
+        if need.value > self._workspace_bytes:
+            self._workspace = None                      # release the old buffer before asking for a bigger one
             self._workspace = self._context.allocate(need.value)
             ptr, _, _ = _device_pointer(self._workspace, "workspace")
             _lib.check(self._lib.b2fft_plan_set_workspace(self._handle, ptr, need.value))
-        self._last_batch_size = batch
+            self._workspace_bytes = need.value
+        self._last_batch_size = key
 
     def _execute(self, wait_for_finish, inverse, batch, in0, in1, out0, out1):
         batch = int(batch)
@@ -210,7 +216,8 @@ class FFTPlan(object):
         if self._split:
             p_in1 = self._check_buffer(in1, "data_in_im", batch)
             p_out1 = self._check_buffer(out1, "data_out_im", batch)
-        self._ensure_workspace(batch)
+        in_place = p_in0 == p_out0 or (self._split and p_in1 == p_out1)
+        self._ensure_workspace(batch, in_place)
         stream = self._context.get_stream()
         _lib.check(self._lib.b2fft_execute(self._handle, p_in0, p_in1, p_out0, p_out1, int(bool(inverse)), batch,
                                            _stream_handle(stream)))

@@ -36,8 +36,8 @@ static void ref_fft(std::vector<cld>& a) {  // in-place recursive radix-2, forwa
     }
 }
 
-template <class Cfg, bool SPLIT, bool INV, int s>
-static void emu_stages(std::vector<TileThread<Cfg, SPLIT, INV>>& th, const PassParams<typename Cfg::T>& p,
+template <class Cfg, bool SPLIT, bool INV, int s, class TH>
+static void emu_stages(std::vector<TH>& th, const PassParams<typename Cfg::T>& p,
                        std::vector<vec2<typename Cfg::T>>& smem) {
     for (auto& t : th) t.template compute<s>(p);
     if constexpr (s + 1 < Cfg::S) {
@@ -220,6 +220,123 @@ static void check_staged(const char* name, long long outer) {
     if (!ok) ++g_fail;
 }
 
+// One pass of the thread program over the arrays `p` points at (plain or four-step "A" mode).
+template <class Cfg, bool SPLIT, bool INV, bool FS>
+static void emu_pass(const PassParams<typename Cfg::T>& p) {
+    using T2 = vec2<typename Cfg::T>;
+    const long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    std::vector<T2> smem((size_t)Cfg::COL_SMEM * Cfg::W * Cfg::G + 1);
+    for (long long bid = 0; bid < ctas; ++bid) {
+        std::vector<TileThread<Cfg, SPLIT, INV, FS>> th(Cfg::THREADS);
+        for (int tid = 0; tid < Cfg::THREADS; ++tid) { th[tid].setup(tid, bid, p); th[tid].load(p); }
+        emu_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
+        for (auto& t : th) t.store(p);
+    }
+}
+
+// Four-step decomposition of an axis of length N = CfgA::N * CfgB::N with element stride inner0:
+// transposing pass A (CfgA, FS mode) followed by the plain strided pass B (CfgB, stride N1*inner0),
+// exactly as api.cu's add_axis()/launch_pass() set them up, against a direct length-N FFT.
+template <class CfgA, class CfgB, bool SPLIT, bool INV>
+static double run_fourstep(long long outer, long long inner0, unsigned seed) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    const long long N1 = CfgA::N, N2 = CfgB::N, N = N1 * N2, total = outer * N * inner0;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T> a_re(total), a_im(total), b_re(total, (T)NAN), b_im(total, (T)NAN);
+    for (long long i = 0; i < total; ++i) { a_re[i] = (T)nd(rng); a_im[i] = (T)nd(rng); }
+    std::vector<T2> a_c(total), b_c(total);
+    for (long long i = 0; i < total; ++i) { a_c[i].x = a_re[i]; a_c[i].y = a_im[i]; b_c[i].x = NAN; b_c[i].y = NAN; }
+    auto set_io = [&](PassParams<T>& p, bool from_a) {
+        if (SPLIT) {
+            p.in0 = from_a ? a_re.data() : b_re.data(); p.in1 = from_a ? a_im.data() : b_im.data();
+            p.out0 = b_re.data(); p.out1 = b_im.data();
+        } else {
+            p.in0 = reinterpret_cast<const T*>(from_a ? a_c.data() : b_c.data());
+            p.out0 = reinterpret_cast<T*>(b_c.data());
+        }
+    };
+    // pass A: [outer][N1][N2*inner0] -> [outer][N2][N1][inner0]
+    {
+        PassParams<T> p{};
+        std::vector<std::vector<T2>> tabs;
+        for (int s = 0; s + 1 < CfgA::S; ++s) tabs.push_back(make_stage_table<T>(CfgA::NS(s), CfgA::R(s)));
+        for (int s = 0; s + 1 < CfgA::S; ++s) p.tw[s] = reinterpret_cast<const T*>(tabs[s].data());
+        auto t1 = make_fs_table<T>(N, N2, CfgA::TPC, 1), t2 = make_fs_table<T>(N, N2, CfgA::E, CfgA::TPC);
+        set_io(p, true);
+        p.inner = N2 * inner0;
+        if (p.inner % CfgA::W) { std::printf("bad inner\n"); std::exit(2); }
+        p.inner_blocks = p.inner / CfgA::W;
+        p.outer_stride = N * inner0;
+        p.n_tiles = outer * p.inner_blocks;
+        p.out_inner = inner0;
+        p.out_outer_stride = p.outer_stride;
+        p.out_blk_log2 = -1;
+        p.scale = 1; p.scale_mode = 0;
+        p.fs_log2_inner = ilog2((int)inner0);
+        p.fs_n2 = N2;
+        p.fs_col_stride = N1 * inner0;
+        p.fs_t1 = reinterpret_cast<const T*>(t1.data());
+        p.fs_t2 = reinterpret_cast<const T*>(t2.data());
+        emu_pass<CfgA, SPLIT, INV, true>(p);
+    }
+    // pass B: [outer][N2][N1*inner0], in place
+    {
+        PassParams<T> p{};
+        std::vector<std::vector<T2>> tabs;
+        for (int s = 0; s + 1 < CfgB::S; ++s) tabs.push_back(make_stage_table<T>(CfgB::NS(s), CfgB::R(s)));
+        for (int s = 0; s + 1 < CfgB::S; ++s) p.tw[s] = reinterpret_cast<const T*>(tabs[s].data());
+        set_io(p, false);
+        p.inner = N1 * inner0;
+        if (p.inner % CfgB::W) { std::printf("bad inner\n"); std::exit(2); }
+        p.inner_blocks = p.inner / CfgB::W;
+        p.outer_stride = N * inner0;
+        p.n_tiles = outer * p.inner_blocks;
+        p.out_inner = p.inner;
+        p.out_outer_stride = p.outer_stride;
+        p.out_blk_log2 = -1;
+        p.scale = (T)0.5; p.scale_mode = 1;
+        emu_pass<CfgB, SPLIT, INV, false>(p);
+    }
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner0; ++i) {
+            for (long long n = 0; n < N; ++n) {
+                const long long idx = (o * N + n) * inner0 + i;
+                line[n] = INV ? cld(a_im[idx], a_re[idx]) : cld(a_re[idx], a_im[idx]);
+            }
+            ref_fft(line);
+            for (long long n = 0; n < N; ++n) {
+                const long long idx = (o * N + n) * inner0 + i;
+                cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+                want *= 0.5L;
+                cld got = SPLIT ? cld(b_re[idx], b_im[idx]) : cld(b_c[idx].x, b_c[idx].y);
+                double e = (double)std::abs(got - want);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(want);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <class CfgA>
+static void check_fourstep(const char* name) {
+    using T = typename CfgA::T;
+    using CfgB = TileCfg<T, 4, (sizeof(T) == 4 ? 16 : 8), (sizeof(T) == 4 ? 8 : 16), 16, 1, 1, 1>;
+    const double tol = sizeof(T) == 4 ? 4e-6 : 2e-14;
+    double e0 = run_fourstep<CfgA, CfgB, false, false>(1, 1, 11);
+    double e1 = run_fourstep<CfgA, CfgB, false, true>(1, 2, 12);
+    double e2 = run_fourstep<CfgA, CfgB, true, false>(2, 2 * CfgA::W, 13);
+    bool ok = e0 < tol && e1 < tol && e2 < tol;
+    std::printf("%-44s four-step N=%dx16  err fwd(i1)=%.2e inv(i2)=%.2e split(i2W)=%.2e %s\n", name, CfgA::N, e0, e1, e2,
+                ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 #define CHKT(T, L, G, R0, R1, R2, R3) \
     check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
 
@@ -229,6 +346,9 @@ static void check_staged(const char* name, long long outer) {
 #define CHK(T, L, W, G, R0, R1, R2, R3, OUTER, INNER) \
     check<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER); \
     if ((W) > 1 && (L) >= 3) check_blocked<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER, (L) >= 8 ? 8 : 2);
+
+#define CHKF(T, L, W, G, R0, R1, R2, R3) \
+    check_fourstep<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3);
 
 int main() {
 #include "emu_cases.inc"
