@@ -66,31 +66,131 @@ constexpr double sin64(int e) {  // e in [0, 32]
     return e <= 16 ? kCosQ64[16 - e] : kCosQ64[e - 16];
 }
 
-// (dr + i di) * exp(-2*pi*i*e/64), e in [0, 32) compile-time.
-template <int e, typename T>
-B2_HD void mul_w64(T dr, T di, T& orr, T& oi) {
+// ------------------------------------------------------------------ complex values in registers
+// cpx<T> is one complex number held by a thread.  For double (and for float on the host, where
+// tests/host_emu runs this code) it is a plain scalar pair.  For float on the device it is ONE
+// 64-bit register pair operated on with Blackwell's packed-FP32 instructions (PTX add/mul/fma
+// .f32x2 -> SASS FADD2 / FMUL2 / FFMA2): a complex add is one instruction instead of two, a
+// complex multiply three instead of four, which is what the radix butterflies are made of.
+// The real/imaginary swap and scalar broadcast these formulas need are operand modifiers of the
+// packed instructions (ptxas folds the mov.b64 re-packs below into .LO_HI / .F32 operands).
+template <typename T> struct cpx { T x, y; };
+template <typename T> struct is_packed { static constexpr bool value = false; };
+#if defined(__CUDA_ARCH__)
+template <> struct cpx<float> { unsigned long long v; };
+template <> struct is_packed<float> { static constexpr bool value = true; };
+#endif
+
+#if defined(__CUDA_ARCH__)
+namespace pk {
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack(float lo, float hi) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ void unpack(u64 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+__device__ __forceinline__ u64 swp(u64 a) { float lo, hi; unpack(a, lo, hi); return pack(hi, lo); }
+__device__ __forceinline__ u64 blo(u64 a) { float lo, hi; unpack(a, lo, hi); return pack(lo, lo); }
+__device__ __forceinline__ u64 bhi(u64 a) { float lo, hi; unpack(a, lo, hi); return pack(hi, hi); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+}  // namespace pk
+#endif
+
+template <typename T> B2_HD cpx<T> cmake(T x, T y) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { cpx<T> c; c.v = pk::pack(x, y); return c; } else
+#endif
+    { cpx<T> c; c.x = x; c.y = y; return c; }
+}
+template <typename T> B2_HD void csplit(const cpx<T>& c, T& x, T& y) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { pk::unpack(c.v, x, y); } else
+#endif
+    { x = c.x; y = c.y; }
+}
+template <typename T> B2_HD cpx<T> cadd(const cpx<T>& a, const cpx<T>& b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { cpx<T> c; c.v = pk::add2(a.v, b.v); return c; } else
+#endif
+    { cpx<T> c; c.x = a.x + b.x; c.y = a.y + b.y; return c; }
+}
+template <typename T> B2_HD cpx<T> csub(const cpx<T>& a, const cpx<T>& b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { cpx<T> c; c.v = pk::sub2(a.v, b.v); return c; } else
+#endif
+    { cpx<T> c; c.x = a.x - b.x; c.y = a.y - b.y; return c; }
+}
+// a * s, s real
+template <typename T> B2_HD cpx<T> cscale(const cpx<T>& a, T s) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { cpx<T> c; c.v = pk::mul2(a.v, pk::pack(s, s)); return c; } else
+#endif
+    { cpx<T> c; c.x = a.x * s; c.y = a.y * s; return c; }
+}
+// a * w (CONJ: a * conj(w)), w a run-time twiddle
+template <bool CONJ, typename T> B2_HD cpx<T> cmul(const cpx<T>& a, const cpx<T>& w) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) {
+        // (ar*wr, ai*wr) -/+ (ai*wi, ar*wi) * (1, -1): three packed instructions
+        const pk::u64 d = pk::mul2(a.v, pk::blo(w.v));
+        const pk::u64 e = pk::mul2(pk::swp(a.v), pk::bhi(w.v));
+        cpx<T> c;
+        c.v = pk::fma2(e, CONJ ? pk::pack(1.0f, -1.0f) : pk::pack(-1.0f, 1.0f), d);
+        return c;
+    } else
+#endif
+    {
+        cpx<T> c;
+        if constexpr (CONJ) { c.x = a.x * w.x + a.y * w.y; c.y = a.y * w.x - a.x * w.y; }
+        else { c.x = a.x * w.x - a.y * w.y; c.y = a.x * w.y + a.y * w.x; }
+        return c;
+    }
+}
+// a * exp(-2*pi*i*e/64) (CONJ: exp(+...)), e in [0, 32) compile-time.
+template <int e, bool CONJ, typename T> B2_HD cpx<T> cmulc(const cpx<T>& a) {
     if constexpr (e == 0) {
-        orr = dr; oi = di;
-    } else if constexpr (e == 16) {
-        orr = di; oi = -dr;
-    } else if constexpr (e == 8) {
-        constexpr T h = (T)0.70710678118654752440;
-        orr = (dr + di) * h; oi = (di - dr) * h;
-    } else if constexpr (e == 24) {
-        constexpr T h = (T)0.70710678118654752440;
-        orr = (di - dr) * h; oi = -(dr + di) * h;
+        return a;
     } else {
-        constexpr T c = (T)cos64(e);
-        constexpr T s = (T)sin64(e);
-        orr = dr * c + di * s;
-        oi = di * c - dr * s;
+#if defined(__CUDA_ARCH__)
+        if constexpr (is_packed<T>::value) {
+            cpx<T> c;
+            if constexpr (e == 16) {        // * -i: (ai, -ar);  * +i: (-ai, ar)
+                c.v = pk::mul2(pk::swp(a.v), CONJ ? pk::pack(-1.0f, 1.0f) : pk::pack(1.0f, -1.0f));
+            } else {                        // (ar*c, ai*c) + (ai, ar) * (s, -s)   [CONJ: (-s, s)]
+                constexpr float cs = (float)cos64(e), sn = (float)sin64(e);
+                c.v = pk::fma2(pk::swp(a.v), CONJ ? pk::pack(-sn, sn) : pk::pack(sn, -sn), pk::mul2(a.v, pk::pack(cs, cs)));
+            }
+            return c;
+        } else
+#endif
+        {
+            cpx<T> c;
+            const T dr = a.x, di = a.y;
+            if constexpr (e == 16) {
+                if constexpr (CONJ) { c.x = -di; c.y = dr; } else { c.x = di; c.y = -dr; }
+            } else if constexpr (e == 8) {
+                constexpr T h = (T)0.70710678118654752440;
+                if constexpr (CONJ) { c.x = (dr - di) * h; c.y = (dr + di) * h; }
+                else { c.x = (dr + di) * h; c.y = (di - dr) * h; }
+            } else if constexpr (e == 24) {
+                constexpr T h = (T)0.70710678118654752440;
+                if constexpr (CONJ) { c.x = -(dr + di) * h; c.y = (dr - di) * h; }
+                else { c.x = (di - dr) * h; c.y = -(dr + di) * h; }
+            } else {
+                constexpr T cs = (T)cos64(e);
+                constexpr T sn = (T)sin64(e);
+                if constexpr (CONJ) { c.x = dr * cs - di * sn; c.y = di * cs + dr * sn; }
+                else { c.x = dr * cs + di * sn; c.y = di * cs - dr * sn; }
+            }
+            return c;
+        }
     }
 }
 
-// In-register forward radix-R DIF FFT on re/im[OFF .. OFF+R).  X[k] ends up at
-// register OFF + brev(k, log2 R) (no data movement for the permutation).
-template <int R, int OFF, typename T>
-B2_HD void butterfly(T* re, T* im) {
+// In-register radix-R DIF FFT on v[OFF .. OFF+R), forward (CONJ: inverse, conjugated roots).
+// X[k] ends up at register OFF + brev(k, log2 R) (no data movement for the permutation).
+template <int R, int OFF, bool CONJ, typename T>
+B2_HD void butterfly(cpx<T>* v) {
     static_assert(R >= 1 && R <= 64 && (R & (R - 1)) == 0, "radix must be a power of two <= 64");
     constexpr int LG = ilog2(R);
     static_for<0, LG>([&](auto lc) {
@@ -101,10 +201,9 @@ B2_HD void butterfly(T* re, T* im) {
             constexpr int ia = OFF + (q / half) * len + (q % half);
             constexpr int ib = ia + half;
             constexpr int e = (q % half) * (64 / len);
-            T ur = re[ia], ui = im[ia], vr = re[ib], vi = im[ib];
-            re[ia] = ur + vr;
-            im[ia] = ui + vi;
-            mul_w64<e>(ur - vr, ui - vi, re[ib], im[ib]);
+            const cpx<T> u = v[ia], w = v[ib];
+            v[ia] = cadd(u, w);
+            v[ib] = cmulc<e, CONJ>(csub(u, w));
         });
     });
 }
@@ -186,19 +285,22 @@ struct TileCfg {
     static constexpr long long SMEM_BYTES = (long long)COL_SMEM * W * G * 2 * sizeof(T);
 };
 
-// ------------------------------------------------------------------ global memory access
+// ------------------------------------------------------------------ memory access
+// streaming global load of one interleaved complex element (bypasses L1 allocation)
 template <typename T>
-B2_HD vec2<T> ld_stream(const vec2<T>* p) {
+B2_HD cpx<T> ld_stream_c(const vec2<T>* p) {
 #if defined(__CUDA_ARCH__)
-    vec2<T> v;
-    if constexpr (sizeof(T) == 4) {
-        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    cpx<T> c;
+    if constexpr (is_packed<T>::value) {
+        asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(c.v) : "l"(p));
+    } else if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(c.x), "=f"(c.y) : "l"(p));
     } else {
-        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(c.x), "=d"(c.y) : "l"(p));
     }
-    return v;
+    return c;
 #else
-    return *p;
+    return cmake<T>(p->x, p->y);
 #endif
 }
 template <typename T>
@@ -215,15 +317,35 @@ B2_HD T ld_stream1(const T* p) {
     return *p;
 #endif
 }
+// plain load / store of one complex element (shared memory, twiddle tables, global stores)
+template <typename T>
+B2_HD cpx<T> ld_c(const vec2<T>* p) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { cpx<T> c; c.v = *reinterpret_cast<const unsigned long long*>(p); return c; } else
+#endif
+    { const vec2<T> v = *p; return cmake<T>(v.x, v.y); }
+}
+template <typename T>
+B2_HD void st_c(vec2<T>* p, const cpx<T>& c) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) { *reinterpret_cast<unsigned long long*>(p) = c.v; } else
+#endif
+    { vec2<T> v; v.x = c.x; v.y = c.y; *p = v; }
+}
 
 // ------------------------------------------------------------------ the thread program
+// INV (interleaved layout only) runs the same program with conjugated roots, i.e. the unscaled
+// inverse DFT.  Split-layout inverses are done by the host swapping the re/im plane pointers
+// (IDFT(z) = swap(DFT(swap z))), so SPLIT kernels are always compiled with INV = false.
 template <class Cfg, bool SPLIT, bool INV, bool FS = false>
 struct TileThread {
     using T = typename Cfg::T;
     using T2 = vec2<T>;
+    using C = cpx<T>;
     static constexpr int E = Cfg::E, N = Cfg::N, W = Cfg::W, S = Cfg::S, TPC = Cfg::TPC;
+    static_assert(!(SPLIT && INV), "split inverses swap the planes on the host");
 
-    T re[E], im[E];
+    C v[E];
     int t, w, g;          // thread-in-column, column-in-tile, tile-in-CTA
     bool active;
     long long base;       // element offset of (n = 0, this column) in the input
@@ -250,29 +372,28 @@ struct TileThread {
         }
     }
 
+    B2_HD void clear() {
+        static_for<0, E>([&](auto jc) { v[decltype(jc)::value] = cmake<T>((T)0, (T)0); });
+    }
+
     // ---- stage 0 input: element n = t + TPC*j  (BPT(0) == 1)
     B2_HD void load(const PassParams<T>& p) {
-        if (!active) {
-            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] = 0; im[decltype(jc)::value] = 0; });
-            return;
-        }
+        if (!active) { clear(); return; }
+        const long long step = (long long)TPC * p.inner;
         if constexpr (SPLIT) {
             const T* pr = p.in0 + base + (long long)t * p.inner;
             const T* pi = p.in1 + base + (long long)t * p.inner;
-            const long long step = (long long)TPC * p.inner;
             static_for<0, E>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                re[j] = ld_stream1(pr + j * step);
-                im[j] = ld_stream1(pi + j * step);
+                const T xr = ld_stream1(pr + j * step);
+                const T xi = ld_stream1(pi + j * step);
+                v[j] = cmake<T>(xr, xi);
             });
         } else {
             const T2* pc = reinterpret_cast<const T2*>(p.in0) + base + (long long)t * p.inner;
-            const long long step = (long long)TPC * p.inner;
             static_for<0, E>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                T2 v = ld_stream(pc + j * step);
-                if constexpr (INV) { re[j] = v.y; im[j] = v.x; }   // IDFT(z) = swap(DFT(swap(z)))
-                else { re[j] = v.x; im[j] = v.y; }
+                v[j] = ld_stream_c(pc + j * step);
             });
         }
     }
@@ -281,26 +402,20 @@ struct TileThread {
     //      the buffer holds the CTA's G tiles densely, tile g at g*N*W, element (n, w) at n*W + w.
     //      SPLIT: `sre`/`sim` are two planes of T; interleaved: `sre` is a vec2<T> array, `sim` unused.
     B2_HD void load_smem(const void* sre, const void* sim) {
-        if (!active) {
-            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] = 0; im[decltype(jc)::value] = 0; });
-            return;
-        }
+        if (!active) { clear(); return; }
         const long long off = ((long long)g * N + t) * W + w;
         if constexpr (SPLIT) {
             const T* pr = static_cast<const T*>(sre) + off;
             const T* pi = static_cast<const T*>(sim) + off;
             static_for<0, E>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                re[j] = pr[j * TPC * W];
-                im[j] = pi[j * TPC * W];
+                v[j] = cmake<T>(pr[j * TPC * W], pi[j * TPC * W]);
             });
         } else {
             const T2* pc = static_cast<const T2*>(sre) + off;
             static_for<0, E>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                const T2 v = pc[j * TPC * W];
-                if constexpr (INV) { re[j] = v.y; im[j] = v.x; }
-                else { re[j] = v.x; im[j] = v.y; }
+                v[j] = ld_c(pc + j * TPC * W);
             });
         }
     }
@@ -309,19 +424,17 @@ struct TileThread {
     template <int s>
     B2_HD void compute(const PassParams<T>& p) {
         constexpr int R = Cfg::R(s);
-        static_for<0, Cfg::BPT(s)>([&](auto ic) { butterfly<R, decltype(ic)::value * R>(re, im); });
+        static_for<0, Cfg::BPT(s)>([&](auto ic) { butterfly<R, decltype(ic)::value * R, INV>(v); });
         if constexpr (s + 1 < S) {
             constexpr int M = Cfg::M(s);
             constexpr int LG = ilog2(R);
             const T2* tw = reinterpret_cast<const T2*>(p.tw[s]) + (t % M);
             static_for<1, R>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                const T2 wv = tw[(k - 1) * M];
+                const C wv = ld_c(tw + (k - 1) * M);
                 static_for<0, Cfg::BPT(s)>([&](auto ic) {
                     constexpr int q = decltype(ic)::value * R + brev(k, LG);
-                    const T xr = re[q], xi = im[q];
-                    re[q] = xr * wv.x - xi * wv.y;
-                    im[q] = xr * wv.y + xi * wv.x;
+                    v[q] = cmul<INV>(v[q], wv);
                 });
             });
         }
@@ -340,8 +453,7 @@ struct TileThread {
             static_for<0, R>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
                 constexpr int q = i * R + brev(k, LG);
-                T2 v; v.x = re[q]; v.y = im[q];
-                dst[(i + k * BPT) * TW * W] = v;
+                st_c(dst + (i + k * BPT) * TW * W, v[q]);
             });
         });
     }
@@ -359,9 +471,7 @@ struct TileThread {
             constexpr int i = decltype(ic)::value;
             static_for<0, R1>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                const T2 v = src[(i * (TPC / M1) * ROWP + j * M1) * W];
-                re[i * R1 + j] = v.x;
-                im[i * R1 + j] = v.y;
+                v[i * R1 + j] = ld_c(src + (i * (TPC / M1) * ROWP + j * M1) * W);
             });
         });
     }
@@ -377,29 +487,26 @@ struct TileThread {
             // inter-pass twiddle w_N^(k1*n2), k1 = t + TPC*c, as the product of two table entries
             const T2* t1p = reinterpret_cast<const T2*>(p.fs_t1) + (long long)t * p.fs_n2 + fs_n2i;
             const T2* t2p = reinterpret_cast<const T2*>(p.fs_t2) + fs_n2i;
-            const T2 b = *t1p;
+            const C b = ld_c(t1p);
             static_for<0, BPT>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 static_for<0, R>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
                     constexpr int q = i * R + brev(k, LG);
                     constexpr int c = i + k * BPT;
-                    T wr = b.x, wi = b.y;
-                    if constexpr (c > 0) {
-                        const T2 sv = t2p[(long long)c * p.fs_n2];
-                        wr = b.x * sv.x - b.y * sv.y;
-                        wi = b.x * sv.y + b.y * sv.x;
-                    }
-                    const T xr = re[q], xi = im[q];
-                    re[q] = xr * wr - xi * wi;
-                    im[q] = xr * wi + xi * wr;
+                    if constexpr (c > 0) v[q] = cmul<INV>(v[q], cmul<false>(b, ld_c(t2p + (long long)c * p.fs_n2)));
+                    else v[q] = cmul<INV>(v[q], b);
                 });
             });
         }
         if (p.scale_mode == 1) {
-            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] *= p.scale; im[decltype(jc)::value] *= p.scale; });
+            static_for<0, E>([&](auto jc) { v[decltype(jc)::value] = cscale(v[decltype(jc)::value], p.scale); });
         } else if (p.scale_mode == 2) {
-            static_for<0, E>([&](auto jc) { re[decltype(jc)::value] /= p.scale; im[decltype(jc)::value] /= p.scale; });
+            static_for<0, E>([&](auto jc) {
+                T xr, xi;
+                csplit(v[decltype(jc)::value], xr, xi);
+                v[decltype(jc)::value] = cmake<T>(xr / p.scale, xi / p.scale);
+            });
         }
         if constexpr (BLK) {
             const int lg = p.out_blk_log2;
@@ -413,13 +520,12 @@ struct TileThread {
                     const int h = n >> lg;
                     const long long off = obase + (long long)(n & mask) * p.out_inner;
                     if constexpr (SPLIT) {
-                        p.out_blk0[h][off] = re[q];
-                        p.out_blk1[h][off] = im[q];
+                        T xr, xi;
+                        csplit(v[q], xr, xi);
+                        p.out_blk0[h][off] = xr;
+                        p.out_blk1[h][off] = xi;
                     } else {
-                        T2 v;
-                        if constexpr (INV) { v.x = im[q]; v.y = re[q]; }
-                        else { v.x = re[q]; v.y = im[q]; }
-                        reinterpret_cast<T2*>(p.out_blk0[h])[off] = v;
+                        st_c(reinterpret_cast<T2*>(p.out_blk0[h]) + off, v[q]);
                     }
                 });
             });
@@ -434,8 +540,10 @@ struct TileThread {
                 static_for<0, R>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
                     constexpr int q = i * R + brev(k, LG);
-                    pr[(i + k * BPT) * step] = re[q];
-                    pi[(i + k * BPT) * step] = im[q];
+                    T xr, xi;
+                    csplit(v[q], xr, xi);
+                    pr[(i + k * BPT) * step] = xr;
+                    pi[(i + k * BPT) * step] = xi;
                 });
             });
         } else {
@@ -445,10 +553,7 @@ struct TileThread {
                 static_for<0, R>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
                     constexpr int q = i * R + brev(k, LG);
-                    T2 v;
-                    if constexpr (INV) { v.x = im[q]; v.y = re[q]; }
-                    else { v.x = re[q]; v.y = im[q]; }
-                    pc[(i + k * BPT) * step] = v;
+                    st_c(pc + (i + k * BPT) * step, v[q]);
                 });
             });
         }
