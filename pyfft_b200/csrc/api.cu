@@ -62,6 +62,7 @@ struct Registry {
         b2::register_f64_col(v);
         n_default = v.size();
         b2::register_exp(v);   // tuning candidates, never picked by default (listed last)
+        b2::register_exp2(v);
         prepared.assign(v.size(), false);
         if (const char* e = getenv("B2FFT_PREFER")) set_preferred(e);
     }

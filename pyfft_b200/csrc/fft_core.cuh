@@ -247,9 +247,14 @@ struct PassParams {
 // ------------------------------------------------------------------ compile-time plan
 // ESZ_ = bytes per complex element in shared memory (8 or 16), used for the
 // bank-conflict padding rule only.
-template <typename T_, int LOG2N_, int W_, int G_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+// TWP_: stage twiddles w^1..w^(R-1) are loaded in full from the table (0) or only w^1..w^3 and
+// w^4, w^8, .. with the rest formed as one product each (1): the tables are read through L1, which
+// shares its data pipe with the shared-memory exchanges that bound these kernels, while the FP
+// pipe has slack (profiles/).  One extra rounding (<= 1 ulp) on 9 of 15 twiddles.
+template <typename T_, int LOG2N_, int W_, int G_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1, int TWP_ = 1>
 struct TileCfg {
     using T = T_;
+    static constexpr int TWP = TWP_;
     static constexpr int LOG2N = LOG2N_;
     static constexpr int N = 1 << LOG2N_;
     static constexpr int W = W_;
@@ -429,14 +434,33 @@ struct TileThread {
             constexpr int M = Cfg::M(s);
             constexpr int LG = ilog2(R);
             const T2* tw = reinterpret_cast<const T2*>(p.tw[s]) + (t % M);
-            static_for<1, R>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                const C wv = ld_c(tw + (k - 1) * M);
-                static_for<0, Cfg::BPT(s)>([&](auto ic) {
-                    constexpr int q = decltype(ic)::value * R + brev(k, LG);
-                    v[q] = cmul<INV>(v[q], wv);
+            if constexpr (Cfg::TWP != 0 && R >= 8) {
+                // w^k = w^(4a) * w^b, k = 4a + b: load w^1..w^3 and w^4, w^8, .., multiply the rest
+                C lo[4], hi[R / 4];
+                static_for<1, 4>([&](auto bc) { lo[decltype(bc)::value] = ld_c(tw + (decltype(bc)::value - 1) * M); });
+                static_for<1, R / 4>([&](auto ac) { hi[decltype(ac)::value] = ld_c(tw + (4 * decltype(ac)::value - 1) * M); });
+                static_for<1, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int a = k / 4, b = k % 4;
+                    C wv;
+                    if constexpr (a == 0) wv = lo[b];
+                    else if constexpr (b == 0) wv = hi[a];
+                    else wv = cmul<false>(hi[a], lo[b]);
+                    static_for<0, Cfg::BPT(s)>([&](auto ic) {
+                        constexpr int q = decltype(ic)::value * R + brev(k, LG);
+                        v[q] = cmul<INV>(v[q], wv);
+                    });
                 });
-            });
+            } else {
+                static_for<1, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    const C wv = ld_c(tw + (k - 1) * M);
+                    static_for<0, Cfg::BPT(s)>([&](auto ic) {
+                        constexpr int q = decltype(ic)::value * R + brev(k, LG);
+                        v[q] = cmul<INV>(v[q], wv);
+                    });
+                });
+            }
         }
     }
 

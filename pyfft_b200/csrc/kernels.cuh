@@ -545,10 +545,22 @@ struct VariantOpsTmaCol {
     out.push_back(::b2::VariantOpsTmaCol<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB, NB, true>::make( \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmac" B2_STR(NB)));
 
+// B2_V0 / B2_VT0 / B2_VC0: tuning variants with the stage twiddles loaded in full (TileCfg::TWP = 0)
+#define B2_V0(T, L, W, G, MB, R0, R1, R2, R3)                                                        \
+    out.push_back(::b2::VariantOps<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3, 0>, MB>::make(            \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tw0"));
+#define B2_VT0(T, L, G, MB, NB, R0, R1, R2, R3)                                                      \
+    out.push_back(::b2::VariantOpsTma<::b2::TileCfg<T, L, 1, G, R0, R1, R2, R3, 0>, MB, NB>::make(     \
+        #T "_n" B2_STR(L) "_w1_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tma" B2_STR(NB) "_tw0"));
+#define B2_VC0(T, L, W, G, MB, NB, R0, R1, R2, R3)                                                   \
+    out.push_back(::b2::VariantOpsTmaCol<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3, 0>, MB, NB>::make(  \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmac" B2_STR(NB) "_tw0"));
+
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);
 void register_f64_row(std::vector<KernelVariant>& out);
 void register_f64_col(std::vector<KernelVariant>& out);
 void register_exp(std::vector<KernelVariant>& out);
+void register_exp2(std::vector<KernelVariant>& out);
 
 }  // namespace b2

@@ -1,10 +1,10 @@
-// Kernel instantiations for group F64_COL (see variants.def).
+// Kernel instantiations for group EXP2 (see variants.def).
 #include "kernels.cuh"
 
 namespace b2 {
-void register_f64_col(std::vector<KernelVariant>& out) {
-#define B2_GROUP_F64_COL
-#define X B2_VB
+void register_exp2(std::vector<KernelVariant>& out) {
+#define B2_GROUP_EXP2
+#define X B2_V
 #define XT B2_VT
 #define XC B2_VC
 #define XF B2_VF

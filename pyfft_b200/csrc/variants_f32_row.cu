@@ -9,11 +9,17 @@ void register_f32_row(std::vector<KernelVariant>& out) {
 #define XC B2_VC
 #define XF B2_VF
 #define XCF B2_VCF
+#define X0 B2_V0
+#define XT0 B2_VT0
+#define XC0 B2_VC0
 #include "variants.def"
 #undef X
 #undef XT
 #undef XC
 #undef XF
 #undef XCF
+#undef X0
+#undef XT0
+#undef XC0
 }
 }  // namespace b2
