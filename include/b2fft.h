@@ -106,6 +106,22 @@ B2FFT_API int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, 
 B2FFT_API int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk0, void* const* blk1,
                                  int64_t out_inner, int64_t out_outer_stride);
 
+/* Slab exchange passes only.  Gives the plan's LAST pass a two-level outer index: its outer index o
+ * (row number for a contiguous-axis pass, [n][inner] block number for a strided pass) is split as
+ * (hi, lo) = (o / outer_div, o % outer_div) and the line/tile starts at
+ *     input:  in  + hi*in_stride_hi  + lo*in_stride_lo
+ *     output: out + hi*out_stride_hi + lo*out_stride_lo      (out = the block pointer when blocked)
+ * in complex elements, instead of o*n*inner.  With it the X pass of the x-slab transform walks the
+ * rows {all local z} x {one chunk of y} of a z-slab and scatters them as [y][z][x-block] into the
+ * ranks' x-slabs.  outer_div = 0 restores the dense index. */
+B2FFT_API int b2fft_plan_set_outer_split(b2fft_plan* plan, int64_t outer_div, int64_t in_stride_lo, int64_t in_stride_hi,
+                               int64_t out_stride_lo, int64_t out_stride_hi);
+
+/* Slab exchange passes only.  Caps the grid of the plan's LAST pass at ctas_per_sm CTAs per SM
+ * (its CTAs then stride over the tiles).  A pass whose stores cross NVLink is link-bound; keeping it
+ * to a sliver of each SM lets the HBM-bound pass of the previous chunk run beside it.  0 = no cap. */
+B2FFT_API int b2fft_plan_set_exchange_ctas(b2fft_plan* plan, int ctas_per_sm);
+
 /* Peer-visible device memory for the slab exchange: plain cudaMalloc'ed buffers whose CUDA IPC
  * handles (64 bytes) can be exchanged between the per-GPU processes (e.g. through
  * torch.distributed.all_gather_object) and opened on the other ranks. */

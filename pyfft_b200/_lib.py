@@ -32,6 +32,8 @@ SIGNATURES = {
     "b2fft_execute": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "b2fft_plan_destroy": (_i, [_vp]),
     "b2fft_plan_set_output_blocks": (_i, [_vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _i64]),
+    "b2fft_plan_set_outer_split": (_i, [_vp, _i64, _i64, _i64, _i64, _i64]),
+    "b2fft_plan_set_exchange_ctas": (_i, [_vp, _i]),
     "b2fft_mem_alloc": (_i, [_sz, _i, ctypes.POINTER(_vp)]),
     "b2fft_mem_free": (_i, [_vp]),
     "b2fft_ipc_export": (_i, [_vp, ctypes.c_char_p]),

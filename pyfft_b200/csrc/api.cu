@@ -274,6 +274,9 @@ struct b2fft_plan {
     void* blk0[B2_MAX_BLOCKS] = {};
     void* blk1[B2_MAX_BLOCKS] = {};
     long long blk_out_inner = 0, blk_out_outer_stride = 0;
+    // two-level outer index of the last pass (b2fft_plan_set_outer_split)
+    int exchange_max_ctas = 0;   // grid cap of the last pass (b2fft_plan_set_exchange_ctas)
+    long long split_div = 0, split_in_lo = 0, split_in_hi = 0, split_out_lo = 0, split_out_hi = 0;
     std::atomic<long long> launches{0};
     int n_transposing = 0;   // four-step "A" passes (cannot run in place)
 };
@@ -383,6 +386,9 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
             (registry().v[vi].kind == 2 && (pitch % 16 != 0 || outer_count > 0x7fffffffLL)))
             vi = ps.fallback;
     }
+    const bool outer_split = last && pl->split_div > 0;
+    if (outer_split && registry().v[vi].kind != 0) vi = ps.fallback;   // TMA staging assumes a dense outer index
+    if (last && pl->nblocks > 0 && !registry().v[vi].blk) vi = ps.fallback;
     const KernelVariant& kv = registry().v[vi];
     b2::PassParams<T> p{};
     if (split && inverse) {   // IDFT(z) = swap(DFT(swap(z))): swap the planes instead of the registers
@@ -417,6 +423,17 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
             p.out_blk0[h] = (T*)(sw ? pl->blk1[h] : pl->blk0[h]);
             p.out_blk1[h] = (T*)(sw ? pl->blk0[h] : pl->blk1[h]);
         }
+    }
+    if (last && pl->exchange_max_ctas > 0) {
+        p.max_ctas = pl->exchange_max_ctas;
+        if (registry().v[vi].kind != 0) return fail(B2FFT_E_UNSUPPORTED, "grid cap needs a plain kernel variant");
+    }
+    if (outer_split) {
+        p.outer_div = pl->split_div;
+        p.outer_stride = pl->split_in_lo;
+        p.in_stride_hi = pl->split_in_hi;
+        p.out_outer_stride = pl->split_out_lo;
+        p.out_stride_hi = pl->split_out_hi;
     }
     p.scale = (T)1;
     p.scale_mode = 0;
@@ -650,7 +667,7 @@ int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk
     if (!blk0 || (split && !blk1)) return fail(B2FFT_E_INVALID, "null block pointer table");
     const Pass& lastp = plan->passes.back();
     if (lastp.n % nblocks) return fail(B2FFT_E_INVALID, "axis length %lld not divisible by %d", lastp.n, nblocks);
-    if (!registry().v[lastp.variant].blk)
+    if (!registry().v[lastp.variant].blk && !registry().v[lastp.fallback].blk)
         return fail(B2FFT_E_UNSUPPORTED, "kernel %s has no destination-blocked store", registry().v[lastp.variant].name);
     for (int h = 0; h < nblocks; ++h) {
         if (!blk0[h] || (split && !blk1[h])) return fail(B2FFT_E_INVALID, "null block pointer %d", h);
@@ -660,6 +677,28 @@ int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk
     plan->nblocks = nblocks;
     plan->blk_out_inner = out_inner;
     plan->blk_out_outer_stride = out_outer_stride;
+    return B2FFT_OK;
+}
+
+int b2fft_plan_set_outer_split(b2fft_plan* plan, int64_t outer_div, int64_t in_stride_lo, int64_t in_stride_hi,
+                               int64_t out_stride_lo, int64_t out_stride_hi) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (outer_div < 0) return fail(B2FFT_E_INVALID, "outer_div must be >= 0");
+    if (outer_div > 0 && plan->passes.empty()) return fail(B2FFT_E_INVALID, "plan has no pass");
+    if (outer_div > 0 && plan->n_transposing > 0) return fail(B2FFT_E_UNSUPPORTED, "outer split on a four-step plan");
+    plan->split_div = outer_div;
+    plan->split_in_lo = in_stride_lo; plan->split_in_hi = in_stride_hi;
+    plan->split_out_lo = out_stride_lo; plan->split_out_hi = out_stride_hi;
+    return B2FFT_OK;
+}
+
+int b2fft_plan_set_exchange_ctas(b2fft_plan* plan, int ctas_per_sm) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (ctas_per_sm < 0) return fail(B2FFT_E_INVALID, "ctas_per_sm must be >= 0");
+    int sms = 0;
+    DeviceGuard guard(plan->device);
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
+    plan->exchange_max_ctas = ctas_per_sm * sms;
     return B2FFT_OK;
 }
 

@@ -232,6 +232,12 @@ struct PassParams {
     int out_blk_log2;        // < 0: plain stores to out0/out1
     T* out_blk0[B2_MAX_BLOCKS];
     T* out_blk1[B2_MAX_BLOCKS];
+    // two-level outer index (slab exchange passes): when outer_div > 0 the outer index o is split as
+    // (o_hi, o_lo) = (o / outer_div, o % outer_div) and the tile starts at
+    //   in:  o_hi*in_stride_hi  + o_lo*outer_stride       out: o_hi*out_stride_hi + o_lo*out_outer_stride
+    // so a pass can walk a sub-range of one axis of a larger array and re-lay-out its result.
+    long long outer_div, in_stride_hi, out_stride_hi;
+    int max_ctas;             // > 0: cap on the grid of the plain kernels (CTAs then stride over the tiles)
     // four-step "A" pass (FS kernels only): the transformed axis of length N = N1*N2 is split as
     // n = n1*N2 + n2; this pass transforms over n1 (length Cfg::N = N1, element stride N2*inner0,
     // so the pass's `inner` is N2*inner0), multiplies output k1 of column n2 by w_N^(k1*n2) and
@@ -366,14 +372,22 @@ struct TileThread {
         long long o = 0, ib = tile;
         if (p.inner_blocks > 1) { o = tile / p.inner_blocks; ib = tile - o * p.inner_blocks; }
         else { o = tile; ib = 0; }
-        base = o * p.outer_stride + ib * W + w;
+        long long obase0;
+        if (p.outer_div > 0) {
+            const long long oh = o / p.outer_div, ol = o - oh * p.outer_div;
+            base = oh * p.in_stride_hi + ol * p.outer_stride + ib * W + w;
+            obase0 = oh * p.out_stride_hi + ol * p.out_outer_stride;
+        } else {
+            base = o * p.outer_stride + ib * W + w;
+            obase0 = o * p.out_outer_stride;
+        }
         if constexpr (FS) {
             const long long c = ib * W + w;                       // column inside [N2][inner0]
             fs_n2i = c >> p.fs_log2_inner;
-            obase = o * p.out_outer_stride + fs_n2i * p.fs_col_stride + (c - (fs_n2i << p.fs_log2_inner));
+            obase = obase0 + fs_n2i * p.fs_col_stride + (c - (fs_n2i << p.fs_log2_inner));
         } else {
             fs_n2i = 0;
-            obase = o * p.out_outer_stride + ib * W + w;
+            obase = obase0 + ib * W + w;
         }
     }
 

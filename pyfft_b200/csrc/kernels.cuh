@@ -32,10 +32,16 @@ tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
     extern __shared__ __align__(16) unsigned char b2_smem_raw[];
     auto* smem = reinterpret_cast<vec2<typename Cfg::T>*>(b2_smem_raw);
     TileThread<Cfg, SPLIT, INV, FS> th;
-    th.setup((int)threadIdx.x, (long long)blockIdx.x, p);
-    th.load(p);
-    run_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
-    th.template store<BLK>(p);
+    // one CTA per G tiles, unless the launch capped the grid (PassParams::max_ctas: exchange passes that
+    // are NVLink-bound leave most of each SM to the kernels they overlap with) -- then CTAs stride
+    const long long n_groups = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    for (long long bid = blockIdx.x; bid < n_groups; bid += gridDim.x) {
+        th.setup((int)threadIdx.x, bid, p);
+        th.load(p);
+        run_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
+        th.template store<BLK>(p);
+        if (bid + (long long)gridDim.x < n_groups) __syncthreads();   // exchange buffer fully read before it is reused
+    }
     if constexpr (BLK) __threadfence_system();   // peer (NVLink) stores visible before the kernel retires
 }
 
@@ -298,7 +304,7 @@ struct VariantOps {
         const long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
         if (ctas <= 0) return cudaSuccess;
         if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
+        const dim3 grid((unsigned)((p.max_ctas > 0 && ctas > p.max_ctas) ? p.max_ctas : ctas)), block(Cfg::THREADS);
         const size_t sm = (size_t)Cfg::SMEM_BYTES;
         if (p.out_blk_log2 >= 0) {
             if constexpr (BLKCAP) go<true, false>(split, inv, grid, block, sm, stream, p);

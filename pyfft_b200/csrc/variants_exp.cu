@@ -9,6 +9,7 @@ void register_exp(std::vector<KernelVariant>& out) {
 #define XC B2_VC
 #define XF B2_VF
 #define XCF B2_VCF
+#define XB B2_VB
 #define X0 B2_V0
 #define XT0 B2_VT0
 #define XC0 B2_VC0
@@ -18,6 +19,7 @@ void register_exp(std::vector<KernelVariant>& out) {
 #undef XC
 #undef XF
 #undef XCF
+#undef XB
 #undef X0
 #undef XT0
 #undef XC0

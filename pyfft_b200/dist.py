@@ -12,6 +12,10 @@ The reference is single-device; both paths here are new f
   the transfer overlaps the butterflies tile by tile and no pack/unpack kernel exists.
   ``exchange="nccl"`` is the baseline: blocked stores into a local send buffer followed by
   ``all_to_all_single``.
+  ``exchange="xslab"`` is the NVLink-efficient fused form: local Y pass first, then the X pass (whose
+  lines are contiguous) scatters every output row as G contiguous X/G-element pieces straight into
+  the peers' buffers, leaving the result x-slab distributed as ``[Y][Z][X/G]``; the X pass runs in
+  y-chunks so the Z pass of chunk c overlaps the NVLink stores of chunk c+1 (see ``SlabPlan``).
 """
 import ctypes
 
@@ -79,6 +83,9 @@ def slab_layout(shape, world_size, rank):
         # inverse: Z pass of rank h writes z-block g to  slab_g + inv_peer_offset, z planes Y*X apart
         "inv_peer_offset": rank * Yb * X,
         "inv_out_inner": Y * X, "inv_out_outer_stride": 0,
+        # "xslab" exchange: the X pass of rank g writes x-block h of row (z, y) to  xslab_h + (y*Z + g*Zl + z)*Xb
+        "Xb": X // G if X % G == 0 else 0, "xslab_elems": Y * Z * (X // G),
+        "xs_peer_offset": rank * Zl * (X // G), "xs_out_stride_y": Z * (X // G), "xs_out_stride_z": X // G,
         # "yzx" y-slab layout [Yb][Z][X]: the Z pass then strides by X only (a Y-pass-like access pattern)
         # instead of Yb*X; the Y pass's stores stride by Z*X between consecutive y instead of X.
         "fwd_peer_offset_yzx": rank * Zl * X, "fwd_out_inner_yzx": Z * X, "fwd_out_outer_stride_yzx": X,
@@ -142,13 +149,13 @@ class SlabPlan(object):
     """
 
     def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
-                 exchange="p2p", device=None, yslab_layout="zyx", chunks=1):
+                 exchange="p2p", device=None, yslab_layout="zyx", chunks=1, exchange_ctas_per_sm=2):
         import torch
         import torch.distributed as dist
         if len(shape) != 3:
             raise ValueError("SlabPlan needs a 3D shape (Z, Y, X)")
-        if exchange not in ("p2p", "nccl"):
-            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange not in ("p2p", "nccl", "xslab"):
+            raise ValueError("exchange must be 'p2p', 'nccl' or 'xslab'")
         if yslab_layout not in ("zyx", "yzx"):
             raise ValueError("yslab_layout must be 'zyx' ([Z][Yb][X]) or 'yzx' ([Yb][Z][X])")
         if yslab_layout == "yzx" and exchange != "p2p":
@@ -157,6 +164,7 @@ class SlabPlan(object):
         # exchange="nccl" only: the slab is processed in `chunks` groups of z planes; the all-to-all of
         # chunk c runs on a side stream while the X/Y passes of chunk c+1 compute
         self.chunks = max(1, int(chunks))
+        self.exchange_ctas_per_sm = int(exchange_ctas_per_sm)
         self._torch, self._dist = torch, dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -181,6 +189,13 @@ class SlabPlan(object):
             return h
 
         X, Y, Z, Zl, Yb = L["X"], L["Y"], L["Z"], L["Zl"], L["Yb"]
+        self._make = make
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+        self._send = None
+        self._fwd_xy = self._fwd_z = self._inv_z = self._inv_xy = None
+        if exchange == "xslab":
+            self._init_xslab()
+            return
         self._fwd_xy = make((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 0)     # forward: scale applied by the Z pass
         yzx = yslab_layout == "yzx"
         if yzx:      # y-slab stored [Yb][Z][X]: the z axis is the middle ("y") axis of that array
@@ -195,9 +210,6 @@ class SlabPlan(object):
         self._yslab_buf = _DeviceBuffer(L["yslab_elems"] * self.esz, self.device)
         self.slab = self._slab_buf.tensor(self.tdtype).view(Zl, Y, X)
         self.yslab = self._yslab_buf.tensor(self.tdtype).view(*((Yb, Z, X) if yzx else (Z, Yb, X)))
-        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
-        self._send = None
-
         G = self.world
         if exchange == "p2p" and G > 1:
             hs = [None] * G
@@ -234,6 +246,97 @@ class SlabPlan(object):
             self._set_blocks(self._fwd_xy, [self._yslab_buf.ptr], L["fwd_out_inner" + sfx], L["fwd_out_outer_stride" + sfx])
             self._set_blocks(self._inv_z, [self._slab_buf.ptr], L["inv_out_inner"], L["inv_out_outer_stride" + sfx])
 
+    # ------------------------------------------------------------------ x-slab mode
+    def _init_xslab(self):
+        """Forward: Y pass (local, in place) -> X pass in y-chunks whose destination-blocked stores put
+        x-block h of every row straight into rank h's x-slab ``[Y][Z][Xb]`` over NVLink (2 KiB
+        contiguous pieces at 2048^3 on 8 GPUs, against the 32-64 byte pieces a strided pass can
+        offer) -> per chunk: cross-rank barrier, Z pass on that chunk's rows (pitch Xb, TMA-staged)
+        while the next chunk's stores are in flight."""
+        torch, dist, L, lib = self._torch, self._dist, self.L, self._lib
+        X, Y, Z, Zl, G = L["X"], L["Y"], L["Z"], L["Zl"], self.world
+        if X % G:
+            raise ValueError("X must be divisible by the number of ranks for the x-slab exchange")
+        Xb = L["Xb"]
+        C = self.chunks if self.chunks > 1 else min(8, Y)
+        while Y % C:
+            C -= 1
+        self.chunks = C
+        Yc = Y // C
+        self._slab_buf = _DeviceBuffer(L["slab_elems"] * self.esz, self.device)
+        self._yslab_buf = _DeviceBuffer(L["xslab_elems"] * self.esz, self.device)
+        self.slab = self._slab_buf.tensor(self.tdtype).view(Zl, Y, X)
+        self.xslab = self._yslab_buf.tensor(self.tdtype).view(Y, Z, Xb)
+        self.yslab = self.xslab                    # the distributed output, whatever its layout
+        if G > 1:
+            hs = [None] * G
+            dist.all_gather_object(hs, self._yslab_buf.handle(), group=self.group)
+            self._peer_yslab = _open_peers(hs, self.rank, self._yslab_buf.ptr, self.device)
+        else:
+            self._peer_yslab = [self._yslab_buf.ptr]
+        self._peer_slab = None
+        mk = self._make
+        self._fwd_y = mk((X, Y, Zl), _lib.AXIS_Y, 0)
+        self._x_plans, self._z_plans = [], []
+        for c in range(C):
+            px = mk((X, Yc, Zl), _lib.AXIS_X, 0)
+            ptrs = [p + ((c * Yc) * Z * Xb + L["xs_peer_offset"]) * self.esz for p in self._peer_yslab]
+            self._set_blocks(px, ptrs, 1, L["xs_out_stride_y"])
+            _lib.check(lib.b2fft_plan_set_outer_split(px, Yc, X, Y * X, L["xs_out_stride_y"], L["xs_out_stride_z"]))
+            if G > 1 and self.exchange_ctas_per_sm > 0:
+                _lib.check(lib.b2fft_plan_set_exchange_ctas(px, self.exchange_ctas_per_sm))
+            self._x_plans.append(px)
+            self._z_plans.append(mk((Xb, Z, Yc), _lib.AXIS_Y, 1))
+        self._chunk_plans = self._x_plans + self._z_plans + [self._fwd_y]
+        self._inv_z = mk((Xb, Z, Y), _lib.AXIS_Y, 0)
+        self._inv_xy = mk((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 1)
+        self._sx = torch.cuda.Stream(device=self.device)
+        self._sz = torch.cuda.Stream(device=self.device, priority=-1)
+        self._events = [torch.cuda.Event() for _ in range(C)]
+        self._Yc = Yc
+
+    def _forward_xslab(self):
+        torch, L = self._torch, self.L
+        cur = torch.cuda.current_stream(self.device)
+        self._sync_ranks()                  # every rank is done with its previous x-slab contents
+        self._exec(self._fwd_y, self._slab_buf.ptr, self._slab_buf.ptr, 0)
+        self._sx.wait_stream(cur)
+        self._sz.wait_stream(cur)
+        row_bytes = L["X"] * self.esz
+        zchunk_bytes = self._Yc * L["Z"] * L["Xb"] * self.esz
+        for c in range(self.chunks):
+            with torch.cuda.stream(self._sx):
+                src = self._slab_buf.ptr + c * self._Yc * row_bytes
+                self._exec(self._x_plans[c], src, src, 0)          # output goes to the block pointers
+                self._sync_ranks()                                 # chunk c of every peer has landed here
+                self._events[c].record(self._sx)
+            with torch.cuda.stream(self._sz):
+                self._sz.wait_event(self._events[c])
+                ptr = self._yslab_buf.ptr + c * zchunk_bytes
+                self._exec(self._z_plans[c], ptr, ptr, 0)
+        cur.wait_stream(self._sx)
+        cur.wait_stream(self._sz)
+        return self.xslab
+
+    def _inverse_xslab(self):
+        """x-slabs -> z-slabs.  Not the timed direction: inverse Z pass in place, an all-to-all of
+        re-packed blocks (torch permute copies + NCCL), inverse X and Y passes."""
+        torch, dist, L, G = self._torch, self._dist, self.L, self.world
+        X, Y, Z, Zl, Xb = L["X"], L["Y"], L["Z"], L["Zl"], L["Xb"]
+        self._sync_ranks()
+        self._exec(self._inv_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 1)
+        send = self.xslab.view(Y, G, Zl, Xb).permute(1, 2, 0, 3).contiguous()        # [g][zl][y][xl]
+        if G > 1:
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(torch_real(recv), torch_real(send), group=self.group)
+        else:
+            recv = send
+        # recv[h][zl][y][xl] -> slab[zl][y][h*Xb + xl]
+        self.slab.view(Zl, Y, G, Xb).copy_(recv.permute(1, 2, 0, 3))
+        del send, recv
+        self._exec(self._inv_xy, self._slab_buf.ptr, self._slab_buf.ptr, 1)
+        return self.slab
+
     # ------------------------------------------------------------------ helpers
     def _set_blocks(self, plan, ptrs, out_inner, out_outer_stride):
         arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
@@ -258,6 +361,8 @@ class SlabPlan(object):
     def forward(self):
         """``plan.slab`` (destroyed) -> ``plan.yslab``.  Asynchronous on the current stream."""
         L, dist = self.L, self._dist
+        if self.exchange == "xslab":
+            return self._forward_xslab()
         self._sync_ranks()                  # every rank is done with its previous y-slab contents
         if self.world > 1 and self.exchange == "nccl":
             # per z-chunk: X pass in place, Y pass with destination-blocked stores into the send buffer,
@@ -287,6 +392,8 @@ class SlabPlan(object):
         """``plan.yslab`` (destroyed) -> ``plan.slab``."""
         L, dist, torch = self.L, self._dist, self._torch
         G = self.world
+        if self.exchange == "xslab":
+            return self._inverse_xslab()
         self._sync_ranks()
         if G > 1 and self.exchange == "nccl":
             self._exec(self._inv_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 1)
@@ -311,7 +418,12 @@ class SlabPlan(object):
             self._lib.b2fft_plan_destroy(h)
         self._chunk_plans = []
         self._send_lists = self._recv_lists = None
-        self.slab = self.yslab = None
+        self.slab = self.yslab = self.xslab = None
+        if self.exchange == "xslab" and getattr(self, "_peer_yslab", None) and self.world > 1:
+            for r, p in enumerate(self._peer_yslab):
+                if r != self.rank:
+                    self._lib.b2fft_ipc_release(p)
+            self._peer_yslab = None
         if getattr(self, "_peer_slab", None):
             for r, p in enumerate(self._peer_slab):
                 if r != self.rank:

@@ -57,6 +57,25 @@ def _blocked_store(L, yfft, send_or_peers, p2p):
                 send_or_peers[h * L["block_elems"] + base:h * L["block_elems"] + base + X] = flat[z, y]
 
 
+def _xslab_blocked_store(L, xfft, peers, chunks):
+    """Emulates the x-slab exchange pass (pyfft_b200/dist.py _init_xslab): the X pass walks the rows
+    {all local z} x {y chunk c} through the two-level outer index given to
+    b2fft_plan_set_outer_split and writes x-block h of each row to peers[h]."""
+    Zl, Y, X, Z, Xb, G = L["Zl"], L["Y"], L["X"], L["Z"], L["Xb"], L["G"]
+    Yc = Y // chunks
+    src = xfft.reshape(-1)
+    for c in range(chunks):
+        in0 = c * Yc * X                                             # pointer offsets the host adds per chunk
+        blk0 = c * Yc * Z * Xb + L["xs_peer_offset"]
+        outer_div, in_lo, in_hi, out_lo, out_hi = Yc, X, Y * X, L["xs_out_stride_y"], L["xs_out_stride_z"]
+        for o in range(Yc * Zl):                                     # the pass's dense row index
+            hi, lo = divmod(o, outer_div)
+            row = src[in0 + hi * in_hi + lo * in_lo:in0 + hi * in_hi + lo * in_lo + X]
+            for h in range(G):
+                off = blk0 + hi * out_hi + lo * out_lo
+                peers[h][off:off + Xb] = row[h * Xb:(h + 1) * Xb]
+
+
 def _worker(rank, world, port, shape, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -104,7 +123,19 @@ def _worker(rank, world, port, shape, q):
                     myslab[off:off + X] = blk[z, yl]
         back = np.fft.ifft(np.fft.ifft(myslab.reshape(L["Zl"], Y, X), axis=1), axis=2)
         err_inv = float(np.abs(back - slab).max())
-        q.put((rank, err_nccl, err_p2p, err_inv))
+        # x-slab exchange: Y pass, then the X pass scatters rows into the ranks' [Y][Z][Xb] x-slabs
+        yx = np.fft.fft(np.fft.fft(slab, axis=1), axis=2)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, yx)
+        minex = np.zeros(L["xslab_elems"], dtype=np.complex128)
+        for src in range(world):
+            Ls = slab_layout(shape, world, src)
+            bufs = [np.zeros(L["xslab_elems"], dtype=np.complex128) if h != rank else minex for h in range(world)]
+            _xslab_blocked_store(Ls, gathered[src], bufs, chunks=2)
+        got3 = np.fft.fft(minex.reshape(Y, Z, L["Xb"]), axis=1)          # Z pass on [Y][Z][Xb]
+        ref3 = want[:, :, rank * L["Xb"]:(rank + 1) * L["Xb"]].transpose(1, 0, 2)
+        err_xs = float(np.abs(got3 - ref3).max() / np.abs(ref3).max())
+        q.put((rank, err_nccl, err_p2p, err_inv, err_xs))
     finally:
         dist.destroy_process_group()
 
@@ -121,5 +152,5 @@ def test_slab_exchange_layout_world2(shape):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, e1, e2, e3 in res:
-        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (rank, e1, e2, e3)
+    for rank, e1, e2, e3, e4 in res:
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12 and e4 < 1e-12, (rank, e1, e2, e3, e4)

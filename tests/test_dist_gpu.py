@@ -37,6 +37,28 @@ def test_slab_plan_single_rank(cuda_device, shape, dtype, layout):
     plan.close()
 
 
+@pytest.mark.parametrize("chunks", [1, 4])
+@pytest.mark.parametrize("shape,dtype", [((32, 64, 128), np.complex64), ((64, 32, 32), np.complex128), ((256, 256, 256), np.complex64),
+                                         ((16, 8, 2048), np.complex64)])
+def test_xslab_plan_single_rank(cuda_device, shape, dtype, chunks):
+    """x-slab exchange mode on one rank: Y pass, chunked X pass with destination-blocked stores through
+    the two-level outer index (b2fft_plan_set_outer_split), chunked Z pass on the [Y][Z][X] result."""
+    import torch
+    from pyfft_b200.dist import SlabPlan
+    plan = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=chunks)
+    x = no.make_input(shape, 1, dtype, seed=19)[0]
+    plan.slab.copy_(torch.from_numpy(x).to(cuda_device))
+    y = plan.forward()
+    torch.cuda.synchronize()
+    want = np.fft.fftn(x.astype(np.complex128))
+    tol = no.tolerance(dtype, int(np.prod(shape)))
+    assert no.rel_l2(y.cpu().numpy().transpose(1, 0, 2), want) < tol
+    back = plan.inverse()
+    torch.cuda.synchronize()
+    assert no.rel_l2(back.cpu().numpy(), x) < tol
+    plan.close()
+
+
 def test_batch_sharded_plan_single_rank(cuda_device):
     import torch
     from pyfft_b200.dist import BatchShardedPlan
@@ -53,10 +75,10 @@ def test_slab_two_ranks_if_available(cuda_device):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "slab_check.py"), "--size", "64", "128",
-           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx", "ncclx4"]
+           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx", "ncclx4", "xslab", "xslabx2"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     recs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
-    assert len(recs) == 8
+    assert len(recs) == 12
     for r in recs:
         assert r["fwd_rel_l2"] < 1e-5 * 21 and r["roundtrip_rel_l2"] < 1e-5 * 21 and r["delta_max_err"] < 1e-4, r

@@ -49,15 +49,27 @@ def main():
                 continue
             yzx = ex.endswith("-yzx")
             chunks = int(ex.split("x")[1]) if ex.startswith("ncclx") else 1          # "ncclx8" = 8 pipelined chunks
-            plan = SlabPlan(shape, dtype=npdt, exchange="nccl" if ex.startswith("nccl") else ex.split("-")[0],
-                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks)
+            xs = ex.startswith("xslab")               # "xslab" / "xslabx4" = 4 y-chunks / "xslabx8c1" = 1 exchange CTA per SM
+            ctas = 2
+            if xs and "c" in ex[5:]:
+                ex_, _, cc = ex.rpartition("c")
+                ctas = int(cc)
+            else:
+                ex_ = ex
+            if xs and "x" in ex_[5:]:
+                chunks = int(ex_[5:].split("x")[1])
+            plan = SlabPlan(shape, dtype=npdt, exchange="xslab" if xs else "nccl" if ex.startswith("nccl") else ex.split("-")[0],
+                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas)
             L = plan.L
             g = torch.Generator(device=dev)
             g.manual_seed(4242 + rank)
             fl = torch.float32 if npdt == np.complex64 else torch.float64
 
             def fill():
-                plan.slab.copy_(torch.view_as_complex(torch.randn(L["Zl"], n, n, 2, dtype=fl, device=dev, generator=g)))
+                zs = max(1, L["Zl"] // 16)
+                for z0 in range(0, L["Zl"], zs):          # in pieces: no slab-sized temporaries
+                    z1 = min(L["Zl"], z0 + zs)
+                    plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, n, n, 2, dtype=fl, device=dev, generator=g)))
             rec = {"n": n, "world": world, "exchange": ex, "dtype": args.dtype}
             fill()
             x_local = plan.slab.clone() if (args.check or n <= 1024) else None
@@ -85,7 +97,9 @@ def main():
                     parts_x, parts_y = [x_local], [plan.yslab]
                 if rank == 0:
                     full = torch.cat(parts_x, dim=0).cpu().numpy()
-                    if yzx:
+                    if xs:          # x-slabs [Y][Z][Xb] side by side along x
+                        got = torch.cat([t.permute(1, 0, 2) for t in parts_y], dim=2).cpu().numpy()
+                    elif yzx:
                         got = torch.cat([t.permute(1, 0, 2) for t in parts_y], dim=1).cpu().numpy()
                     else:
                         got = torch.cat(parts_y, dim=1).cpu().numpy()      # y-slabs side by side
@@ -135,6 +149,8 @@ def main():
                 rec["sent_bytes_per_gpu"] = L["slab_elems"] * npdt.itemsize * (world - 1) / world
                 rec["nvlink_gbs_per_gpu_if_exchange_were_all"] = rec["sent_bytes_per_gpu"] / (ms * 1e-3) / 1e9
             plan.close()
+            del plan
+            torch.cuda.empty_cache()
             if rank == 0:
                 print(json.dumps(rec), flush=True)
                 results.append(rec)
