@@ -35,6 +35,9 @@ WORKLOADS = {
     "cfg2s": ((4096,), 65536, "float32", 1, "1D split float32 re/im N=4096 batch=65536 normalize=True"),
     "cfg3": ((1024, 1024), 256, "complex64", 2, "2D complex64 1024x1024 batch=256"),
     "cfg4": ((256, 256, 256), 1, "complex128", 3, "3D complex128 256^3 fast_math off"),
+    # one big transform: N=1 runs an ordinary in-place Plan, N>1 the x-slab decomposition (strong scaling)
+    "cfg5": ((2048, 2048, 2048), 1, "complex64", 3, "3D complex64 2048^3, slab-decomposed over the ranks (x-slab exchange over NVLink)"),
+    "cfg5s": ((512, 512, 512), 1, "complex64", 3, "3D complex64 512^3 slab-decomposed (small stand-in for cfg5)"),
 }
 
 
@@ -223,6 +226,99 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
+def run_slab(args):
+    """cfg5: ONE 3D transform.  N=1: Plan.execute in place; N>1: pyfft_b200.dist.SlabPlan (x-slab exchange).
+    Strong scaling: value = 5 N log2 N / t with t the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from pyfft_b200.cuda import Plan
+    from pyfft_b200.dist import SlabPlan
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    shape, _, dtype, passes, desc = WORKLOADS[args.workload]
+    n = shape[0]
+    size = float(np.prod(shape))
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    launches = [0]
+    if world == 1:
+        a = torch.empty(shape, dtype=torch.complex64, device=dev)
+        ar = torch.view_as_real(a)
+        for z in range(0, n, 64):
+            ar[z:z + 64].normal_(generator=g)
+        plan = Plan(shape, dtype=np.complex64, stream=torch.cuda.current_stream(dev), wait_for_finish=False)
+        desc_plan = plan.passes
+
+        def step():
+            plan.execute(a)
+        count = lambda: plan.launch_count
+    else:
+        plan = SlabPlan(shape, dtype=np.complex64, exchange="xslab", chunks=8, exchange_ctas_per_sm=3)
+        zs = max(1, plan.L["Zl"] // 16)
+        for z0 in range(0, plan.L["Zl"], zs):
+            z1 = min(plan.L["Zl"], z0 + zs)
+            plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, n, n, 2, device=dev, generator=g)))
+        desc_plan = ["x-slab: Y pass, 8 x (X pass with NVLink-blocked stores | barrier | Z pass)"]
+
+        def step():
+            plan.forward()
+        count = lambda: plan.launch_count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= args.steps
+    value = 5.0 * size * math.log2(size) / (ms * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    per_gpu_bytes = 2.0 * 8 * size / world                 # one pass over this rank's share: read + write
+    achieved = passes * per_gpu_bytes / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(per_gpu_bytes), "launches_per_step": passes,
+                "note": "whole step (3 passes over this rank's share) / step time; at N>1 the step is NVLink-bound"}
+    if world > 1:
+        sent = 8.0 * size / world * (world - 1) / world
+        roofline["nvlink"] = {"sent_bytes_per_gpu": int(sent), "achieved_gbs_if_step_were_all_exchange": round(sent / (ms * 1e-3) / 1e9, 1),
+                              "peak_gbs": 770.0, "peak_source": "B200_PROFILING.md measured peer copy per direction"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "in_place": True, "l2": "data exceeds the 126 MB L2; no flush needed",
+                       "plan": desc_plan, "parallelism": "z-slabs over %d GPU(s), output x-slab distributed" % world if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": int(count() - l0), "clocks": clocks}), flush=True)
+    if world > 1:
+        plan.close()
+        dist.destroy_process_group()
+
+
 def run_b2fft(args):
     import torch
     import torch.distributed as dist
@@ -394,10 +490,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=16)
-    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("cfg5", "cfg5s"):
+        run_slab(args)
     else:
         run_b2fft(args)
 
