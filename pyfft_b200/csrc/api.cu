@@ -80,7 +80,9 @@ struct Registry {
     // rows of the transformed axis are >= 256 KiB apart (Z passes of large 3-D arrays) every row
     // access pays a DRAM-page / TLB miss, throughput scales with the contiguous segment width, and the
     // widest tile wins regardless of staging (W=16: 59-74 %, W=8: 37-46 %, W=4: ~20 % of peak).
-    int pick(int prec, int log2n, bool contiguous, long long inner) {
+    // Split re/im rows prefer the TMA-staged kernels: the two planes arrive as two bulk copies instead of
+    // twice the number of 4-byte global loads (measured, profiles/r01_sweep_split.txt).
+    int pick(int prec, int log2n, bool contiguous, long long inner, bool split = false) {
         auto ok = [&](const KernelVariant& k) {
             if (k.prec != prec || k.log2n != log2n) return false;
             if (contiguous) return k.W == 1;
@@ -96,6 +98,9 @@ struct Registry {
                 if (ok(v[i]) && v[i].kind == 0 && (best < 0 || v[i].W > v[best].W)) best = (int)i;
             if (best >= 0) return best;
         }
+        if (contiguous && split)
+            for (size_t i = 0; i < n_default; ++i)
+                if (ok(v[i]) && v[i].kind == 1) return (int)i;
         for (size_t i = 0; i < v.size(); ++i)
             if (ok(v[i])) return (int)i;
         if (!contiguous) return pick_direct_w1(prec, log2n);   // narrow inner dimension: one column per tile
@@ -299,7 +304,7 @@ int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
     Registry& reg = registry();
     const int lg = ilog2ll(n);
     const bool fs = fs_total > 0;
-    int vi = fs ? reg.pick_fs(pl->prec, lg, inner) : reg.pick(pl->prec, lg, contiguous, inner);
+    int vi = fs ? reg.pick_fs(pl->prec, lg, inner) : reg.pick(pl->prec, lg, contiguous, inner, pl->layout == B2FFT_SPLIT);
     if (vi < 0)
         return fail(B2FFT_E_UNSUPPORTED, "no kernel for axis %c of length %lld (%s) in this build", "xyz"[axis], n,
                     pl->prec ? "f64" : "f32");
@@ -419,10 +424,19 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
         p.out_inner = pl->blk_out_inner;
         p.out_outer_stride = pl->blk_out_outer_stride;
         const bool sw = split && inverse;
+        bool aligned = true;
         for (int h = 0; h < pl->nblocks; ++h) {
             p.out_blk0[h] = (T*)(sw ? pl->blk1[h] : pl->blk0[h]);
             p.out_blk1[h] = (T*)(sw ? pl->blk0[h] : pl->blk1[h]);
+            aligned = aligned && ((uintptr_t)p.out_blk0[h] % 16) == 0;
         }
+        // contiguous-axis exchange pass: every (line, block) piece is contiguous -> TMA bulk stores
+        static const bool bulk_ok = [] { const char* e = getenv("B2FFT_BLK_BULK"); return !e || atoi(e) != 0; }();
+        const long long piece = (ps.n / pl->nblocks) * (long long)(2 * sizeof(T));
+        const long long lo = pl->split_div > 0 ? pl->split_out_lo : pl->blk_out_outer_stride;
+        const long long hi = pl->split_div > 0 ? pl->split_out_hi : 0;
+        p.blk_bulk = bulk_ok && !split && kv.W == 1 && kv.S > 1 && ps.inner == 1 && pl->blk_out_inner == 1 && aligned &&
+                     piece % 16 == 0 && (lo * (long long)(2 * sizeof(T))) % 16 == 0 && (hi * (long long)(2 * sizeof(T))) % 16 == 0;
     }
     if (last && pl->exchange_max_ctas > 0) {
         p.max_ctas = pl->exchange_max_ctas;

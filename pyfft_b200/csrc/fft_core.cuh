@@ -237,6 +237,7 @@ struct PassParams {
     //   in:  o_hi*in_stride_hi  + o_lo*outer_stride       out: o_hi*out_stride_hi + o_lo*out_outer_stride
     // so a pass can walk a sub-range of one axis of a larger array and re-lay-out its result.
     long long outer_div, in_stride_hi, out_stride_hi;
+    int blk_bulk;             // blocked stores of a contiguous-axis pass go out as TMA bulk copies (kernels.cuh)
     int max_ctas;             // > 0: cap on the grid of the plain kernels (CTAs then stride over the tiles)
     // four-step "A" pass (FS kernels only): the transformed axis of length N = N1*N2 is split as
     // n = n1*N2 + n2; this pass transforms over n1 (length Cfg::N = N1, element stride N2*inner0,
@@ -514,6 +515,28 @@ struct TileThread {
         });
     }
 
+    // ---- scale / normalise (last pass only; pyfft/kernel.py:23-37)
+    B2_HD void apply_scale(const PassParams<T>& p) {
+        if (p.scale_mode == 1) {
+            static_for<0, E>([&](auto jc) { v[decltype(jc)::value] = cscale(v[decltype(jc)::value], p.scale); });
+        } else if (p.scale_mode == 2) {
+            static_for<0, E>([&](auto jc) {
+                T xr, xi;
+                csplit(v[decltype(jc)::value], xr, xi);
+                v[decltype(jc)::value] = cmake<T>(xr / p.scale, xi / p.scale);
+            });
+        }
+    }
+
+    // output element offset of tile `tile` (contiguous-axis passes: one line per tile)
+    static B2_HD long long line_out_base(long long tile, const PassParams<T>& p) {
+        if (p.outer_div > 0) {
+            const long long oh = tile / p.outer_div, ol = tile - oh * p.outer_div;
+            return oh * p.out_stride_hi + ol * p.out_outer_stride;
+        }
+        return tile * p.out_outer_stride;
+    }
+
     // ---- final output: n = t + TPC*(i + k*BPT) in natural order, scaled.
     //      BLK: destination-blocked stores (see PassParams::out_blk_log2).
     template <bool BLK = false>
@@ -537,15 +560,7 @@ struct TileThread {
                 });
             });
         }
-        if (p.scale_mode == 1) {
-            static_for<0, E>([&](auto jc) { v[decltype(jc)::value] = cscale(v[decltype(jc)::value], p.scale); });
-        } else if (p.scale_mode == 2) {
-            static_for<0, E>([&](auto jc) {
-                T xr, xi;
-                csplit(v[decltype(jc)::value], xr, xi);
-                v[decltype(jc)::value] = cmake<T>(xr / p.scale, xi / p.scale);
-            });
-        }
+        apply_scale(p);
         if constexpr (BLK) {
             const int lg = p.out_blk_log2;
             const int mask = (1 << lg) - 1;

@@ -23,6 +23,51 @@ __device__ __forceinline__ void run_stages(TH& th, const PassParams<typename Cfg
     }
 }
 
+// Destination-blocked output of a contiguous-axis pass as TMA bulk copies (SASS UBLKCP): the finished
+// lines are laid out densely in shared memory and every (line, block) piece -- N/nblocks contiguous
+// elements -- leaves as ONE cp.async.bulk to the block's buffer, which in the x-slab exchange is a peer
+// GPU's memory over NVLink.  The copy engine of the SM moves kilobyte pieces instead of the LSU moving
+// 256 bytes per warp instruction, and no thread stalls on a remote store.
+template <class Cfg, bool INV>
+__device__ __forceinline__ void store_blocked_bulk(TileThread<Cfg, false, INV, false>& th,
+                                                   const PassParams<typename Cfg::T>& p, vec2<typename Cfg::T>* smem,
+                                                   long long bid) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    constexpr int N = Cfg::N, TPC = Cfg::TPC, S = Cfg::S;
+    constexpr int R = Cfg::R(S - 1), LG = ilog2(R), BPT = Cfg::BPT(S - 1);
+    __syncthreads();                                   // the last exchange has been read by everyone
+    th.apply_scale(p);
+    if (th.active) {
+        T2* dst = smem + (long long)th.g * N + th.t;
+        static_for<0, BPT>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            static_for<0, R>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                st_c(dst + (i + k * BPT) * TPC, th.v[i * R + brev(k, LG)]);
+            });
+        });
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy reads
+    __syncthreads();
+    const int lg = p.out_blk_log2;
+    const int nb = N >> lg;
+    const unsigned bytes = (unsigned)(sizeof(T2) << lg);
+    for (int i = (int)threadIdx.x; i < Cfg::G * nb; i += Cfg::THREADS) {
+        const int g = i / nb, h = i - g * nb;
+        const long long tile = bid * Cfg::G + g;
+        if (tile < p.n_tiles) {
+            T2* gdst = reinterpret_cast<T2*>(p.out_blk0[h]) + TileThread<Cfg, false, INV, false>::line_out_base(tile, p);
+            const T2* ssrc = smem + (long long)g * N + ((long long)h << lg);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                         "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                         : "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused (after a barrier)
+}
+
 // BLK: destination-blocked stores (slab exchange); FS: four-step "A" pass (transposed store +
 // inter-pass twiddle, see PassParams).  The two are never combined.
 template <class Cfg, bool SPLIT, bool INV, int MINB, bool BLK = false, bool FS = false>
@@ -39,10 +84,18 @@ tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
         th.setup((int)threadIdx.x, bid, p);
         th.load(p);
         run_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
-        th.template store<BLK>(p);
+        bool bulk = false;
+        if constexpr (BLK && Cfg::W == 1 && Cfg::S > 1 && !SPLIT) bulk = p.blk_bulk != 0;
+        if constexpr (BLK && Cfg::W == 1 && Cfg::S > 1 && !SPLIT) {
+            if (bulk) store_blocked_bulk<Cfg, INV>(th, p, smem, bid);
+        }
+        if (!bulk) th.template store<BLK>(p);
         if (bid + (long long)gridDim.x < n_groups) __syncthreads();   // exchange buffer fully read before it is reused
     }
-    if constexpr (BLK) __threadfence_system();   // peer (NVLink) stores visible before the kernel retires
+    if constexpr (BLK) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // bulk stores of this thread have completed
+        __threadfence_system();                                      // peer (NVLink) stores visible before the kernel retires
+    }
 }
 
 // ------------------------------------------------------------------ persistent TMA-fed kernel (contiguous axis)
