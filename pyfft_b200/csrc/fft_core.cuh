@@ -237,6 +237,7 @@ struct PassParams {
     //   in:  o_hi*in_stride_hi  + o_lo*outer_stride       out: o_hi*out_stride_hi + o_lo*out_outer_stride
     // so a pass can walk a sub-range of one axis of a larger array and re-lay-out its result.
     long long outer_div, in_stride_hi, out_stride_hi;
+    int tma_store;            // strided persistent kernels: output tiles leave as TMA tensor stores (kernels.cuh)
     int blk_bulk;             // blocked stores of a contiguous-axis pass go out as TMA bulk copies (kernels.cuh)
     int max_ctas;             // > 0: cap on the grid of the plain kernels (CTAs then stride over the tiles)
     // four-step "A" pass (FS kernels only): the transformed axis of length N = N1*N2 is split as

@@ -224,6 +224,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 template <class Cfg>
 struct TmaColBox {
     static constexpr int NB = Cfg::N < 256 ? Cfg::N : 256;     // rows per TMA box (box dims are <= 256)
@@ -233,7 +239,8 @@ struct TmaColBox {
 template <class Cfg, bool SPLIT, bool INV, int MINB, int NBUF, bool BLK, bool FS = false>
 __global__ void __launch_bounds__(Cfg::THREADS, MINB)
 tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, const __grid_constant__ CUtensorMap tm0,
-                        const __grid_constant__ CUtensorMap tm1) {
+                        const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tmo0,
+                        const __grid_constant__ CUtensorMap tmo1) {
     using T = typename Cfg::T;
     using T2 = vec2<T>;
     using L = TmaRowLayout<Cfg, NBUF>;                 // same ring / exchange / barrier layout (IN_BYTES = G*N*W complex)
@@ -290,13 +297,80 @@ tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, c
         th.load_smem(src, src + L::IN_BYTES / 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // see tile_fft_kernel_tma_row
         mbar_arrive(&empty[slot]);
+        if constexpr (!BLK && !FS) {
+            // the previous tile's tensor stores have finished reading the exchange buffer
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         __syncthreads();
         if (tid == 0 && grp + (long long)NBUF * stride < n_groups) {
             mbar_wait(&empty[slot], (it / NBUF) & 1);
             issue(grp + (long long)NBUF * stride, slot);
         }
         run_stages<Cfg, SPLIT, INV, 0>(th, p, xbuf);
+        if constexpr (!BLK && !FS) {
+            if (p.tma_store) {
+                // Output through the TMA unit as well: the finished tiles are laid out densely ([N][W], the box
+                // layout) in the exchange buffer and leave as cp.async.bulk.tensor stores (SASS UTMASTG).  A
+                // warp-wide st.global of a W-wide tile touches 4-8 different 128-byte lines (one L1 wavefront
+                // each); the shared-memory store is 2 wavefronts and the strided scatter costs no LSU time.
+                __syncthreads();                                   // the last exchange has been read by everyone
+                th.apply_scale(p);
+                if (th.active) {
+                    constexpr int S_ = Cfg::S, R_ = Cfg::R(S_ - 1), LG_ = ilog2(R_), BPT_ = Cfg::BPT(S_ - 1);
+                    const long long off = ((long long)th.g * Cfg::N + th.t) * Cfg::W + th.w;
+                    if constexpr (SPLIT) {
+                        T* sre = reinterpret_cast<T*>(xbuf) + off;
+                        T* sim = sre + (size_t)Cfg::G * Cfg::N * Cfg::W;
+                        static_for<0, BPT_>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            static_for<0, R_>([&](auto kc) {
+                                constexpr int k = decltype(kc)::value;
+                                T xr, xi;
+                                csplit(th.v[i * R_ + brev(k, LG_)], xr, xi);
+                                sre[(i + k * BPT_) * Cfg::TPC * Cfg::W] = xr;
+                                sim[(i + k * BPT_) * Cfg::TPC * Cfg::W] = xi;
+                            });
+                        });
+                    } else {
+                        T2* sc = xbuf + off;
+                        static_for<0, BPT_>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            static_for<0, R_>([&](auto kc) {
+                                constexpr int k = decltype(kc)::value;
+                                st_c(sc + (i + k * BPT_) * Cfg::TPC * Cfg::W, th.v[i * R_ + brev(k, LG_)]);
+                            });
+                        });
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    long long tiles = p.n_tiles - grp * Cfg::G;
+                    if (tiles > Cfg::G) tiles = Cfg::G;
+                    for (int g = 0; g < (int)tiles; ++g) {
+                        const long long tile = grp * Cfg::G + g;
+                        const long long o = tile / p.inner_blocks, ib = tile - o * p.inner_blocks;
+#pragma unroll
+                        for (int nb = 0; nb < NLOAD; ++nb) {
+                            if constexpr (SPLIT) {
+                                const T* s0 = reinterpret_cast<const T*>(xbuf) + ((size_t)g * Cfg::N + (size_t)nb * NB) * Cfg::W;
+                                tma_store_3d(&tmo0, s0, (int)(ib * Cfg::W), nb * NB, (int)o);
+                                tma_store_3d(&tmo1, s0 + (size_t)Cfg::G * Cfg::N * Cfg::W, (int)(ib * Cfg::W), nb * NB, (int)o);
+                            } else {
+                                const T2* s0 = xbuf + ((size_t)g * Cfg::N + (size_t)nb * NB) * Cfg::W;
+                                tma_store_3d(&tmo0, s0, (int)(ib * Cfg::W * 2), nb * NB, (int)o);
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
+        }
         th.template store<BLK>(p);
+    }
+    if constexpr (!BLK && !FS) {
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // tensor stores have completed
     }
     if constexpr (BLK) __threadfence_system();
 }
@@ -521,11 +595,11 @@ struct VariantOpsTmaCol {
     }
     template <bool SPLIT, bool INV>
     static void go(bool blk, dim3 grid, dim3 block, size_t sm, cudaStream_t st, const PassParams<T>& p, const CUtensorMap& a,
-                   const CUtensorMap& b) {
-        if (blk) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, true><<<grid, block, sm, st>>>(p, a, b);
+                   const CUtensorMap& b, const CUtensorMap& oa, const CUtensorMap& ob) {
+        if (blk) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, true><<<grid, block, sm, st>>>(p, a, b, oa, ob);
         else if (p.fs_t1 != nullptr) {
-            if constexpr (FSCAP) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false, true><<<grid, block, sm, st>>>(p, a, b);
-        } else tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false><<<grid, block, sm, st>>>(p, a, b);
+            if constexpr (FSCAP) tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false, true><<<grid, block, sm, st>>>(p, a, b, oa, ob);
+        } else tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, false><<<grid, block, sm, st>>>(p, a, b, oa, ob);
     }
     static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
         const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
@@ -546,9 +620,26 @@ struct VariantOpsTmaCol {
         const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
         const bool blk = p.out_blk_log2 >= 0;
         if (!FSCAP && p.fs_t1 != nullptr) return cudaErrorNotSupported;
-        if (split) go<true, false>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
-        else if (inv) go<false, true>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
-        else go<false, false>(blk, grid, block, L::TOTAL, stream, p, tm0, tm1);
+        // output maps for the tensor-store path (plain passes only; same geometry as the input)
+        alignas(64) CUtensorMap tmo0 = tm0, tmo1 = tm1;
+        PassParams<T> q = p;
+        q.tma_store = 0;
+        static const bool ts_ok = [] { const char* e = getenv("B2FFT_TMA_STORE"); return !e || atoi(e) != 0; }();
+        if (ts_ok && !blk && p.fs_t1 == nullptr && p.outer_div == 0 && p.out_inner == p.inner &&
+            p.out_outer_stride == p.outer_stride && ((uintptr_t)p.out0 % 16) == 0 && (!split || ((uintptr_t)p.out1 % 16) == 0)) {
+            q.tma_store = 1;
+            if (p.out0 != p.in0) {
+                e = b2_make_col_map<T>(&tmo0, p.out0, split ? 1 : 2, p.inner, Cfg::N, outer, Cfg::W, NB);
+                if (e != cudaSuccess) return e;
+            }
+            if (split && p.out1 != p.in1) {
+                e = b2_make_col_map<T>(&tmo1, p.out1, 1, p.inner, Cfg::N, outer, Cfg::W, NB);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        if (split) go<true, false>(blk, grid, block, L::TOTAL, stream, q, tm0, tm1, tmo0, tmo1);
+        else if (inv) go<false, true>(blk, grid, block, L::TOTAL, stream, q, tm0, tm1, tmo0, tmo1);
+        else go<false, false>(blk, grid, block, L::TOTAL, stream, q, tm0, tm1, tmo0, tmo1);
         return cudaGetLastError();
     }
     static int occupancy() {
