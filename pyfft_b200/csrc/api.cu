@@ -416,6 +416,12 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
         p.fs_col_stride = ps.n * ps.inner0;
         p.fs_t1 = (const T*)(vi == ps.variant ? ps.fs_t1 : ps.fs_t1_fb);
         p.fs_t2 = (const T*)(vi == ps.variant ? ps.fs_t2 : ps.fs_t2_fb);
+        // contiguous axis: whole transposed output rows leave as bulk copies (16-byte alignment rules)
+        static const bool fsb_ok = [] { const char* e = getenv("B2FFT_FS_BULK"); return !e || atoi(e) != 0; }();
+        // measured (profiles/r01_tma_store_fs_bulk.md): +33..42 % for N = 2^16..2^18, +18 % at 2^24, a few % at
+        // 2^20; the 2048-row x W=4 TMA tiles of 2^22 lose 7 % and keep their direct stores
+        p.fs_bulk = fsb_ok && !split && ps.inner0 == 1 && kv.S > 1 && ((uintptr_t)out0 % 16) == 0 &&
+                    (ps.n * (long long)(2 * sizeof(T))) % 16 == 0 && !(kv.kind == 2 && kv.log2n >= 11);
     }
     if (last && pl->nblocks > 0) {
         if (!kv.blk) return fail(B2FFT_E_UNSUPPORTED, "kernel %s has no destination-blocked store", kv.name);

@@ -237,6 +237,7 @@ struct PassParams {
     //   in:  o_hi*in_stride_hi  + o_lo*outer_stride       out: o_hi*out_stride_hi + o_lo*out_outer_stride
     // so a pass can walk a sub-range of one axis of a larger array and re-lay-out its result.
     long long outer_div, in_stride_hi, out_stride_hi;
+    int fs_bulk;              // four-step pass A, inner0 == 1: whole output rows leave as cp.async.bulk (kernels.cuh)
     int tma_store;            // strided persistent kernels: output tiles leave as TMA tensor stores (kernels.cuh)
     int blk_bulk;             // blocked stores of a contiguous-axis pass go out as TMA bulk copies (kernels.cuh)
     int max_ctas;             // > 0: cap on the grid of the plain kernels (CTAs then stride over the tiles)
@@ -294,7 +295,10 @@ struct TileCfg {
         for (int s = 0; s + 1 < S; ++s) m = PADN(s) > m ? PADN(s) : m;
         return m;
     }
-    static constexpr int COL_SMEM = max_padn();                 // complex elements per column
+    // complex elements per column: the largest exchange, plus 16 bytes so that the four-step pass can
+    // stage its output transposed with a bank-conflict-free, 16-byte aligned row pitch (kernels.cuh)
+    static constexpr int FS_PADE = 16 / (2 * (int)sizeof(T_));
+    static constexpr int COL_SMEM = max_padn() > 0 ? max_padn() + FS_PADE : 0;
     static constexpr long long SMEM_BYTES = (long long)COL_SMEM * W * G * 2 * sizeof(T);
 };
 
@@ -516,6 +520,25 @@ struct TileThread {
         });
     }
 
+    // ---- four-step pass A: inter-pass twiddle w_N^(k1*n2), k1 = t + TPC*c, as the product of two table entries
+    B2_HD void apply_fs_twiddle(const PassParams<T>& p) {
+        constexpr int s = S - 1;
+        constexpr int R = Cfg::R(s), LG = ilog2(R), BPT = Cfg::BPT(s);
+        const T2* t1p = reinterpret_cast<const T2*>(p.fs_t1) + (long long)t * p.fs_n2 + fs_n2i;
+        const T2* t2p = reinterpret_cast<const T2*>(p.fs_t2) + fs_n2i;
+        const C b = ld_c(t1p);
+        static_for<0, BPT>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            static_for<0, R>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr int q = i * R + brev(k, LG);
+                constexpr int c = i + k * BPT;
+                if constexpr (c > 0) v[q] = cmul<INV>(v[q], cmul<false>(b, ld_c(t2p + (long long)c * p.fs_n2)));
+                else v[q] = cmul<INV>(v[q], b);
+            });
+        });
+    }
+
     // ---- scale / normalise (last pass only; pyfft/kernel.py:23-37)
     B2_HD void apply_scale(const PassParams<T>& p) {
         if (p.scale_mode == 1) {
@@ -545,22 +568,7 @@ struct TileThread {
         if (!active) return;
         constexpr int s = S - 1;
         constexpr int R = Cfg::R(s), LG = ilog2(R), BPT = Cfg::BPT(s);
-        if constexpr (FS) {
-            // inter-pass twiddle w_N^(k1*n2), k1 = t + TPC*c, as the product of two table entries
-            const T2* t1p = reinterpret_cast<const T2*>(p.fs_t1) + (long long)t * p.fs_n2 + fs_n2i;
-            const T2* t2p = reinterpret_cast<const T2*>(p.fs_t2) + fs_n2i;
-            const C b = ld_c(t1p);
-            static_for<0, BPT>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                static_for<0, R>([&](auto kc) {
-                    constexpr int k = decltype(kc)::value;
-                    constexpr int q = i * R + brev(k, LG);
-                    constexpr int c = i + k * BPT;
-                    if constexpr (c > 0) v[q] = cmul<INV>(v[q], cmul<false>(b, ld_c(t2p + (long long)c * p.fs_n2)));
-                    else v[q] = cmul<INV>(v[q], b);
-                });
-            });
-        }
+        if constexpr (FS) apply_fs_twiddle(p);
         apply_scale(p);
         if constexpr (BLK) {
             const int lg = p.out_blk_log2;

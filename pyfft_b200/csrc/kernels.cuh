@@ -68,6 +68,49 @@ __device__ __forceinline__ void store_blocked_bulk(TileThread<Cfg, false, INV, f
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused (after a barrier)
 }
 
+// Four-step pass A on a contiguous axis (inner0 == 1): column w of the tile becomes the N1 contiguous
+// outputs [n2][k1 = 0..N1).  The tile is staged TRANSPOSED in shared memory (row pitch N1 + 16 bytes:
+// conflict-free for the column-major writes, 16-byte aligned for the copy) and every row leaves as ONE
+// cp.async.bulk of N1 complex elements, instead of 32-byte pieces per warp store.
+template <class Cfg, bool INV>
+__device__ __forceinline__ void store_fs_bulk(TileThread<Cfg, false, INV, true>& th, const PassParams<typename Cfg::T>& p,
+                                              vec2<typename Cfg::T>* smem, long long first_tile) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    constexpr int N = Cfg::N, W = Cfg::W, TPC = Cfg::TPC, S = Cfg::S;
+    constexpr int R = Cfg::R(S - 1), LG = ilog2(R), BPT = Cfg::BPT(S - 1);
+    constexpr int P = N + Cfg::FS_PADE;                // staged row pitch in complex elements
+    static_assert((long long)P * W <= (long long)Cfg::COL_SMEM * W, "staging fits the exchange buffer");
+    __syncthreads();                                   // the last exchange has been read by everyone
+    th.apply_fs_twiddle(p);
+    if (th.active) {
+        T2* dst = smem + ((long long)th.g * W + th.w) * P + th.t;
+        static_for<0, BPT>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            static_for<0, R>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                st_c(dst + (i + k * BPT) * TPC, th.v[i * R + brev(k, LG)]);
+            });
+        });
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    for (int i = (int)threadIdx.x; i < Cfg::G * W; i += Cfg::THREADS) {
+        const int g = i / W, w = i - g * W;
+        const long long tile = first_tile + g;
+        if (tile < p.n_tiles) {
+            const long long o = tile / p.inner_blocks, ib = tile - o * p.inner_blocks;
+            T2* gdst = reinterpret_cast<T2*>(p.out0) + o * p.out_outer_stride + (ib * W + w) * p.fs_col_stride;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                         "r"((uint32_t)__cvta_generic_to_shared(smem + ((long long)g * W + w) * P)),
+                         "r"((unsigned)(N * sizeof(T2)))
+                         : "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused (after a barrier)
+}
+
 // BLK: destination-blocked stores (slab exchange); FS: four-step "A" pass (transposed store +
 // inter-pass twiddle, see PassParams).  The two are never combined.
 template <class Cfg, bool SPLIT, bool INV, int MINB, bool BLK = false, bool FS = false>
@@ -85,17 +128,19 @@ tile_fft_kernel(const __grid_constant__ PassParams<typename Cfg::T> p) {
         th.load(p);
         run_stages<Cfg, SPLIT, INV, 0>(th, p, smem);
         bool bulk = false;
-        if constexpr (BLK && Cfg::W == 1 && Cfg::S > 1 && !SPLIT) bulk = p.blk_bulk != 0;
         if constexpr (BLK && Cfg::W == 1 && Cfg::S > 1 && !SPLIT) {
+            bulk = p.blk_bulk != 0;
             if (bulk) store_blocked_bulk<Cfg, INV>(th, p, smem, bid);
+        }
+        if constexpr (FS && Cfg::S > 1 && !SPLIT) {
+            bulk = p.fs_bulk != 0;
+            if (bulk) store_fs_bulk<Cfg, INV>(th, p, smem, bid * Cfg::G);
         }
         if (!bulk) th.template store<BLK>(p);
         if (bid + (long long)gridDim.x < n_groups) __syncthreads();   // exchange buffer fully read before it is reused
     }
-    if constexpr (BLK) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // bulk stores of this thread have completed
-        __threadfence_system();                                      // peer (NVLink) stores visible before the kernel retires
-    }
+    if constexpr (BLK || FS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's bulk stores are done
+    if constexpr (BLK) __threadfence_system();      // peer (NVLink) stores visible before the kernel retires
 }
 
 // ------------------------------------------------------------------ persistent TMA-fed kernel (contiguous axis)
@@ -367,11 +412,18 @@ tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, c
                 continue;
             }
         }
+        if constexpr (FS && Cfg::S > 1 && !SPLIT) {
+            if (p.fs_bulk) {
+                store_fs_bulk<Cfg, INV>(th, p, xbuf, grp * Cfg::G);
+                continue;
+            }
+        }
         th.template store<BLK>(p);
     }
     if constexpr (!BLK && !FS) {
         if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // tensor stores have completed
     }
+    if constexpr (FS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if constexpr (BLK) __threadfence_system();
 }
 
@@ -624,7 +676,9 @@ struct VariantOpsTmaCol {
         alignas(64) CUtensorMap tmo0 = tm0, tmo1 = tm1;
         PassParams<T> q = p;
         q.tma_store = 0;
-        static const bool ts_ok = [] { const char* e = getenv("B2FFT_TMA_STORE"); return !e || atoi(e) != 0; }();
+        // measured on B200 (profiles/r01_tma_store_fs_bulk.md): -3 % on N=1024 x W=8 tiles, +1 % on N=2048 x W=4 --
+        // the extra barrier and shared-memory pass cancel the saved L1 wavefronts, so it is opt-in
+        static const bool ts_ok = [] { const char* e = getenv("B2FFT_TMA_STORE"); return e && atoi(e) != 0; }();
         if (ts_ok && !blk && p.fs_t1 == nullptr && p.outer_div == 0 && p.out_inner == p.inner &&
             p.out_outer_stride == p.outer_stride && ((uintptr_t)p.out0 % 16) == 0 && (!split || ((uintptr_t)p.out1 % 16) == 0)) {
             q.tma_store = 1;
