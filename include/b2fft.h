@@ -141,6 +141,10 @@ B2FFT_API int b2fft_stream_synchronize(void* cuda_stream);
 B2FFT_API int b2fft_plan_num_passes(const b2fft_plan* plan);
 /* One line per pass: "axis=X n=4096 inner=1 variant=float_n12_w1_..." */
 B2FFT_API int b2fft_plan_describe(const b2fft_plan* plan, char* buf, size_t buflen);
+/* The pass list b2fft_plan_create would build for these dimensions (same text as
+ * b2fft_plan_describe), without touching a device: which axes run as one pass, which are split
+ * four-step style ("fs=N1xN2" marks the transposing pass) and which kernel variant each pass uses. */
+B2FFT_API int b2fft_plan_preview(const int64_t dims_xyz[3], int axes_mask, int precision, int layout, char* buf, size_t buflen);
 /* Number of kernels this plan has launched since creation (bench.py's gpu_launches). */
 B2FFT_API int64_t b2fft_plan_launch_count(const b2fft_plan* plan);
 

@@ -42,6 +42,7 @@ SIGNATURES = {
     "b2fft_stream_synchronize": (_i, [_vp]),
     "b2fft_plan_num_passes": (_i, [_vp]),
     "b2fft_plan_describe": (_i, [_vp, ctypes.c_char_p, _sz]),
+    "b2fft_plan_preview": (_i, [ctypes.POINTER(_i64), _i, _i, _i, ctypes.c_char_p, _sz]),
     "b2fft_plan_launch_count": (_i64, [_vp]),
     "b2fft_num_variants": (_i, []),
     "b2fft_variant_info": (_i, [_i, ctypes.c_char_p, _sz]),

@@ -284,11 +284,13 @@ struct b2fft_plan {
     long long split_div = 0, split_in_lo = 0, split_in_hi = 0, split_out_lo = 0, split_out_hi = 0;
     std::atomic<long long> launches{0};
     int n_transposing = 0;   // four-step "A" passes (cannot run in place)
+    bool dry = false;        // b2fft_plan_preview: plan the passes only, no device work
 };
 
 namespace {
 
 int stage_tables(b2fft_plan* pl, const KernelVariant& kv, long long n, const void** tw) {
+    if (pl->dry) return 0;
     int NS = (int)n;
     for (int s = 0; s + 1 < kv.S; ++s) {
         int rc = twiddles().get(pl->device, pl->prec, NS, kv.radix[s], &tw[s]);
@@ -319,13 +321,13 @@ int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
     p.inner = inner;
     int rc = stage_tables(pl, kv, n, p.tw);
     if (rc) return rc;
-    cudaError_t e = reg.prepare(vi);
+    cudaError_t e = pl->dry ? cudaSuccess : reg.prepare(vi);
     if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
     const KernelVariant& fb = reg.v[p.fallback];
     if (p.fallback != vi) {
         rc = stage_tables(pl, fb, n, p.tw_fb);
         if (rc) return rc;
-        e = reg.prepare(p.fallback);
+        e = pl->dry ? cudaSuccess : reg.prepare(p.fallback);
         if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
     } else {
         for (int s = 0; s < 3; ++s) p.tw_fb[s] = p.tw[s];
@@ -335,7 +337,7 @@ int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
         p.fs_total = fs_total;
         p.fs_n2 = fs_total / n;
         p.inner0 = inner0;
-        for (int which = 1; which <= 2; ++which) {
+        for (int which = 1; which <= 2 && !pl->dry; ++which) {
             rc = fs_twiddles().get(pl->device, pl->prec, which, fs_total, p.fs_n2, (int)(n / kv.E), kv.E,
                                    which == 1 ? &p.fs_t1 : &p.fs_t2);
             if (rc) return rc;
@@ -785,6 +787,23 @@ int b2fft_plan_describe(const b2fft_plan* plan, char* buf, size_t buflen) {
     }
     snprintf(buf, buflen, "%s", s.c_str());
     return B2FFT_OK;
+}
+
+int b2fft_plan_preview(const int64_t dims_xyz[3], int axes_mask, int precision, int layout, char* buf, size_t buflen) {
+    if (!dims_xyz || !buf || !buflen) return fail(B2FFT_E_INVALID, "bad argument");
+    for (int a = 0; a < 3; ++a)
+        if (!is_pow2(dims_xyz[a])) return fail(B2FFT_E_INVALID, "Array dimensions must be powers of two");
+    if (precision != B2FFT_F32 && precision != B2FFT_F64) return fail(B2FFT_E_INVALID, "bad precision %d", precision);
+    if (layout != B2FFT_INTERLEAVED && layout != B2FFT_SPLIT) return fail(B2FFT_E_INVALID, "bad layout %d", layout);
+    if (axes_mask < 0 || axes_mask > 7) return fail(B2FFT_E_INVALID, "bad axes mask %d", axes_mask);
+    b2fft_plan pl;
+    pl.dry = true;
+    pl.x = dims_xyz[0]; pl.y = dims_xyz[1]; pl.z = dims_xyz[2];
+    pl.axes_mask = axes_mask; pl.prec = precision; pl.layout = layout; pl.device = -1;
+    pl.normalize = 1; pl.fast_math = 1; pl.scale = 1.0; pl.norm_size = 1.0; pl.apply_scale = 1;
+    int rc = build_passes(&pl);
+    if (rc) return rc;
+    return b2fft_plan_describe(&pl, buf, buflen);
 }
 
 int64_t b2fft_plan_launch_count(const b2fft_plan* plan) { return plan ? (int64_t)plan->launches.load() : -1; }

@@ -1,0 +1,77 @@
+"""CPU tests of the host planner (no GPU): b2fft_plan_preview builds the pass list exactly as
+b2fft_plan_create does.  One pass per axis while the axis fits one CTA; longer axes are split
+four-step style (the counterpart of the reference's local-vs-global decision, pyfft/plan.py:141-167,
+and its base-128 chains, pyfft/kernel_helpers.py:67-122)."""
+import ctypes
+import re
+
+import pytest
+
+
+def _preview(lib, x, y=1, z=1, prec=0, layout=0, mask=7):
+    buf = ctypes.create_string_buffer(4096)
+    from pyfft_b200 import _lib
+    _lib.check(lib.b2fft_plan_preview((ctypes.c_int64 * 3)(x, y, z), mask, prec, layout, buf, len(buf)))
+    out = []
+    for line in buf.value.decode().splitlines():
+        m = re.match(r"axis=(\w) n=(\d+) inner=(\d+) variant=(\S+)(?: fs=(\d+)x(\d+))?", line)
+        assert m, line
+        out.append({"axis": m.group(1), "n": int(m.group(2)), "inner": int(m.group(3)), "variant": m.group(4),
+                    "fs": (int(m.group(5)), int(m.group(6))) if m.group(5) else None})
+    return out
+
+
+def test_one_pass_per_axis_when_it_fits(built_lib):
+    for prec, xmax in ((0, 1 << 14), (1, 1 << 13)):
+        p = _preview(built_lib, xmax, 2048, 2048, prec=prec)
+        assert [(q["axis"], q["n"], q["inner"]) for q in p] == [("X", xmax, 1), ("Y", 2048, xmax), ("Z", 2048, xmax * 2048)]
+        assert all(q["fs"] is None for q in p)
+    assert _preview(built_lib, 1, 1, 1) == []                                    # nothing to do
+    assert [q["axis"] for q in _preview(built_lib, 8, 1, 16)] == ["X", "Z"]       # size-1 axes are no-ops
+    assert [q["axis"] for q in _preview(built_lib, 64, 64, 64, mask=2)] == ["Y"]  # axis masks (slab plans)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("lg", [14, 15, 16, 20, 22, 23, 24, 27])
+def test_long_contiguous_axis_is_split(built_lib, prec, lg):
+    n = 1 << lg
+    p = _preview(built_lib, n, prec=prec)
+    if lg <= (14 if prec == 0 else 13):
+        assert len(p) == 1 and p[0]["fs"] is None
+        return
+    assert len(p) == (2 if lg <= 22 else 3)
+    # the factors multiply to n; every transposing pass carries the twiddle of the axis it splits
+    prod, inner, remaining = 1, 1, n
+    for q in p[:-1]:
+        n1, n2 = q["fs"]
+        assert q["n"] == n1 and n1 * n2 == remaining and q["inner"] == n2 * inner
+        prod, inner, remaining = prod * n1, inner * n1, n2
+    assert p[-1]["fs"] is None and p[-1]["n"] == remaining and p[-1]["inner"] == inner
+    assert prod * p[-1]["n"] == n
+    assert all(q["n"] <= 2048 for q in p)
+
+
+def test_long_strided_axis_is_split(built_lib):
+    p = _preview(built_lib, 64, 4096, 1)
+    assert [(q["axis"], q["n"], q["inner"], q["fs"]) for q in p] == [("X", 64, 1, None), ("Y", 64, 64 * 64, (64, 64)),
+                                                                  ("Y", 64, 64 * 64, None)]
+    p = _preview(built_lib, 4096, 8, 4096)
+    assert [q["axis"] for q in p] == ["X", "Y", "Z", "Z"] and p[2]["fs"] == (64, 64)
+
+
+def test_layout_and_pitch_aware_variant_choice(built_lib):
+    # split-layout rows take the TMA-staged kernel, interleaved rows the plain high-occupancy one
+    assert "_tma" in _preview(built_lib, 4096, layout=1)[0]["variant"]
+    assert "_tma" not in _preview(built_lib, 4096, layout=0)[0]["variant"]
+    # strided axes: TMA tensor staging for N >= 1024 unless rows are >= 256 KiB apart
+    assert "_tmac" in _preview(built_lib, 1024, 1024)[1]["variant"]
+    z = _preview(built_lib, 2048, 2048, 2048)[2]
+    assert "_tmac" not in z["variant"] and "_w8_" in z["variant"]
+
+
+def test_preview_validation(built_lib):
+    from pyfft_b200 import _lib
+    buf = ctypes.create_string_buffer(64)
+    assert built_lib.b2fft_plan_preview((ctypes.c_int64 * 3)(12, 1, 1), 7, 0, 0, buf, len(buf)) == _lib.E_INVALID
+    assert "powers of two" in _lib.last_error()
+    assert built_lib.b2fft_plan_preview((ctypes.c_int64 * 3)(16, 1, 1), 7, 3, 0, buf, len(buf)) == _lib.E_INVALID
