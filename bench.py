@@ -124,21 +124,30 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
+def host_threads():
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU
+    arms are meant to use the whole host, so the thread count is passed to the C port explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_rate(shape, dtype, target_seconds=6.0, max_batch=65536):
     """Times oracle/pyfft_port.c (the restated reference algorithm, all host threads) on a bounded
     batch of the same transform; returns (GFLOP/s, threads, sample description, seconds)."""
     from oracle import numpy_oracle as no
     from oracle import pyfft_port as pp
-    threads = pp.max_threads()
+    threads = host_threads()
     size = int(np.prod(shape))
     b = max(threads * 4, 64)
     b = min(b, max_batch)
     x = no.make_input(shape, b, dtype, seed=1)
     if isinstance(x, tuple):
         x = (x[0] + 1j * x[1]).astype(np.complex64 if x[0].dtype == np.float32 else np.complex128)
-    pp.execute(x, shape, b)                                   # warm-up (thread pool, page faults)
+    pp.execute(x, shape, b, nthreads=threads)                                   # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    pp.execute(x, shape, b)
+    pp.execute(x, shape, b, nthreads=threads)
     dt = time.perf_counter() - t0
     b2 = int(min(max_batch, max(b, b * target_seconds / max(dt, 1e-6))))
     if b2 > b * 2:
@@ -146,7 +155,7 @@ def cpu_port_rate(shape, dtype, target_seconds=6.0, max_batch=65536):
         x = np.tile(x, (reps,) + (1,) * (x.ndim - 1))
         b = b * reps
         t0 = time.perf_counter()
-        pp.execute(x, shape, b)
+        pp.execute(x, shape, b, nthreads=threads)
         dt = time.perf_counter() - t0
     rate = flops(shape, b) / dt / 1e9
     return rate, threads, "batch=%d of shape %s (%d elements), %.2f s wall on %d threads" % (
@@ -189,15 +198,15 @@ def run_reference(args):
         return
     shape, batch, dtype, passes, desc = WORKLOADS[args.workload]
     from oracle import pyfft_port as pp
-    threads = pp.max_threads()
+    threads = host_threads()
     # bounded sample per step: sized from a calibration run so one step is ~1.5 s
     from oracle import numpy_oracle as no
     cdt = np.complex64 if np.dtype(dtype) in (np.dtype(np.complex64), np.dtype(np.float32)) else np.complex128
     b = min(batch, max(threads * 4, 64))
     x = no.make_input(shape, b, cdt, seed=1)
-    pp.execute(x, shape, b)
+    pp.execute(x, shape, b, nthreads=threads)
     t0 = time.perf_counter()
-    pp.execute(x, shape, b)
+    pp.execute(x, shape, b, nthreads=threads)
     dt = time.perf_counter() - t0
     reps = int(max(1, min(batch // b, 1.5 / max(dt, 1e-6))))
     if reps > 1:
@@ -205,10 +214,10 @@ def run_reference(args):
         b *= reps
     out = np.empty_like(x)
     for _ in range(args.warmup):
-        pp.execute(x, shape, b, out=out)
+        pp.execute(x, shape, b, out=out, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pp.execute(x, shape, b, out=out)
+        pp.execute(x, shape, b, out=out, nthreads=threads)
     el = time.perf_counter() - t0
     rate = flops(shape, b) * args.steps / el / 1e9
     sample = "each step = batch %d of %s (of the workload's %d), pyfft algorithm restated in C, OpenMP over lines" % (
