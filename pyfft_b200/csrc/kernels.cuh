@@ -427,6 +427,88 @@ tile_fft_kernel_tma_col(const __grid_constant__ PassParams<typename Cfg::T> p, c
     if constexpr (BLK) __threadfence_system();
 }
 
+// ------------------------------------------------------------------ TMA-staged strided kernel, ring slot == exchange buffer
+// The big strided tiles (N = 1024/2048) leave room for only ONE CTA per SM when the TMA ring and the
+// exchange buffer are separate, so that CTA's load, compute and store phases never overlap with anything
+// but its own prefetch.  Here the single staging slot IS the exchange buffer: half the shared memory, two
+// CTAs per SM, and the phases of one CTA overlap with those of the other.  The next tile's TMA load is
+// issued as soon as every thread has finished the last exchange read (generic -> async proxy fence +
+// "empty" mbarrier), i.e. it runs under this CTA's last butterflies and stores.
+template <class Cfg>
+struct TmaAliasLayout {
+    using T = typename Cfg::T;
+    static constexpr size_t IN_BYTES = (size_t)Cfg::G * Cfg::N * Cfg::W * 2 * sizeof(T);
+    static constexpr size_t X_BYTES = ((size_t)Cfg::SMEM_BYTES + 127) / 128 * 128;
+    static constexpr size_t BUF_BYTES = IN_BYTES > X_BYTES ? IN_BYTES : X_BYTES;
+    static constexpr size_t BAR_OFF = BUF_BYTES;               // full, empty
+    static constexpr size_t TOTAL = BAR_OFF + 16;
+};
+
+template <class Cfg, bool SPLIT, bool INV, int MINB, bool BLK>
+__global__ void __launch_bounds__(Cfg::THREADS, MINB)
+tile_fft_kernel_tma_col_alias(const __grid_constant__ PassParams<typename Cfg::T> p, const __grid_constant__ CUtensorMap tm0,
+                              const __grid_constant__ CUtensorMap tm1) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    using L = TmaAliasLayout<Cfg>;
+    constexpr int NB = TmaColBox<Cfg>::NB, NLOAD = TmaColBox<Cfg>::NLOAD;
+    extern __shared__ __align__(128) unsigned char b2_smem_raw[];
+    T2* xbuf = reinterpret_cast<T2*>(b2_smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(b2_smem_raw + L::BAR_OFF);
+    uint64_t* empty = full + 1;
+    const int tid = (int)threadIdx.x;
+    const long long n_groups = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    const long long stride = gridDim.x;
+
+    auto issue = [&](long long grp) {
+        long long tiles = p.n_tiles - grp * Cfg::G;
+        if (tiles > Cfg::G) tiles = Cfg::G;
+        constexpr uint32_t plane_bytes = (uint32_t)(Cfg::N * Cfg::W * sizeof(T));
+        mbar_expect_tx(full, (uint32_t)tiles * 2u * plane_bytes);
+        for (int g = 0; g < (int)tiles; ++g) {
+            const long long tile = grp * Cfg::G + g;
+            const long long o = tile / p.inner_blocks, ib = tile - o * p.inner_blocks;
+#pragma unroll
+            for (int nb = 0; nb < NLOAD; ++nb) {
+                if constexpr (SPLIT) {
+                    unsigned char* d0 = b2_smem_raw + ((size_t)g * Cfg::N + (size_t)nb * NB) * Cfg::W * sizeof(T);
+                    tma_load_3d(d0, &tm0, (int)(ib * Cfg::W), nb * NB, (int)o, full);
+                    tma_load_3d(d0 + L::IN_BYTES / 2, &tm1, (int)(ib * Cfg::W), nb * NB, (int)o, full);
+                } else {
+                    unsigned char* d0 = b2_smem_raw + ((size_t)g * Cfg::N + (size_t)nb * NB) * Cfg::W * 2 * sizeof(T);
+                    tma_load_3d(d0, &tm0, (int)(ib * Cfg::W * 2), nb * NB, (int)o, full);
+                }
+            }
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(full, 1);
+        mbar_init(empty, Cfg::THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long grp = blockIdx.x;
+    if (tid == 0 && grp < n_groups) issue(grp);
+    TileThread<Cfg, SPLIT, INV, false> th;
+    for (unsigned it = 0; grp < n_groups; ++it, grp += stride) {
+        th.setup(tid, grp, p);
+        mbar_wait(full, it & 1);
+        th.load_smem(b2_smem_raw, b2_smem_raw + L::IN_BYTES / 2);
+        __syncthreads();                       // the staged tile is in registers everywhere: the buffer may be overwritten
+        run_stages<Cfg, SPLIT, INV, 0>(th, p, xbuf);
+        // hand the buffer to the async proxy for the next tile (see tile_fft_kernel_tma_row for the fence)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(empty);
+        if (tid == 0 && grp + stride < n_groups) {
+            mbar_wait(empty, it & 1);
+            issue(grp + stride);
+        }
+        th.template store<BLK>(p);
+    }
+    if constexpr (BLK) __threadfence_system();
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -717,6 +799,84 @@ struct VariantOpsTmaCol {
     }
 };
 
+template <class Cfg, int MINB>
+struct VariantOpsTmaColAlias {
+    using T = typename Cfg::T;
+    using L = TmaAliasLayout<Cfg>;
+    static int& slots() { static int s = 0; return s; }
+    template <bool SPLIT, bool INV, bool BLK>
+    static cudaError_t attr() {
+        return cudaFuncSetAttribute(tile_fft_kernel_tma_col_alias<Cfg, SPLIT, INV, MINB, BLK>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+    }
+    static cudaError_t prepare() {
+        cudaError_t e;
+        if ((e = attr<false, false, false>()) != cudaSuccess) return e;
+        if ((e = attr<false, true, false>()) != cudaSuccess) return e;
+        if ((e = attr<true, false, false>()) != cudaSuccess) return e;
+        if ((e = attr<false, false, true>()) != cudaSuccess) return e;
+        if ((e = attr<false, true, true>()) != cudaSuccess) return e;
+        if ((e = attr<true, false, true>()) != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_fft_kernel_tma_col_alias<Cfg, false, false, MINB, false>,
+                                                          Cfg::THREADS, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return b2_get_encode_tiled() ? cudaSuccess : cudaErrorNotSupported;
+    }
+    template <bool SPLIT, bool INV>
+    static void go(bool blk, dim3 grid, dim3 block, cudaStream_t st, const PassParams<T>& p, const CUtensorMap& a,
+                   const CUtensorMap& b) {
+        if (blk) tile_fft_kernel_tma_col_alias<Cfg, SPLIT, INV, MINB, true><<<grid, block, L::TOTAL, st>>>(p, a, b);
+        else tile_fft_kernel_tma_col_alias<Cfg, SPLIT, INV, MINB, false><<<grid, block, L::TOTAL, st>>>(p, a, b);
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+        if (ctas <= 0) return cudaSuccess;
+        if (p.fs_t1 != nullptr) return cudaErrorNotSupported;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        if (ctas > slots()) ctas = slots();
+        const long long outer = p.n_tiles / p.inner_blocks;
+        constexpr int NB = TmaColBox<Cfg>::NB;
+        alignas(64) CUtensorMap tm0, tm1;
+        cudaError_t e = b2_make_col_map<T>(&tm0, p.in0, split ? 1 : 2, p.inner, Cfg::N, outer, Cfg::W, NB);
+        if (e != cudaSuccess) return e;
+        tm1 = tm0;
+        if (split) {
+            e = b2_make_col_map<T>(&tm1, p.in1, 1, p.inner, Cfg::N, outer, Cfg::W, NB);
+            if (e != cudaSuccess) return e;
+        }
+        const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
+        const bool blk = p.out_blk_log2 >= 0;
+        if (split) go<true, false>(blk, grid, block, stream, p, tm0, tm1);
+        else if (inv) go<false, true>(blk, grid, block, stream, p, tm0, tm1);
+        else go<false, false>(blk, grid, block, stream, p, tm0, tm1);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_fft_kernel_tma_col_alias<Cfg, false, false, MINB, false>,
+                                                          Cfg::THREADS, L::TOTAL) != cudaSuccess)
+            return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v = VariantOps<Cfg, MINB, false>::make(name);
+        v.smem_bytes = (long long)L::TOTAL;
+        v.kind = 2;
+        v.nbuf = 0;
+        v.blk = 1;
+        v.fs = 0;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        return v;
+    }
+};
+
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x
 #define B2_STR(x) B2_STR2(x)
@@ -759,6 +919,11 @@ struct VariantOpsTmaCol {
 #define B2_VC0(T, L, W, G, MB, NB, R0, R1, R2, R3)                                                   \
     out.push_back(::b2::VariantOpsTmaCol<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3, 0>, MB, NB>::make(  \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmac" B2_STR(NB) "_tw0"));
+
+// B2_VCA(type, log2n, W, G, minblocks, R0..R3): TMA-staged strided variant whose staging slot is the exchange buffer
+#define B2_VCA(T, L, W, G, MB, R0, R1, R2, R3)                                                       \
+    out.push_back(::b2::VariantOpsTmaColAlias<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB>::make(    \
+        #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmaca"));
 
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);

@@ -10,6 +10,7 @@ void register_exp(std::vector<KernelVariant>& out) {
 #define XF B2_VF
 #define XCF B2_VCF
 #define XB B2_VB
+#define XCA B2_VCA
 #define X0 B2_V0
 #define XT0 B2_VT0
 #define XC0 B2_VC0
@@ -20,6 +21,7 @@ void register_exp(std::vector<KernelVariant>& out) {
 #undef XF
 #undef XCF
 #undef XB
+#undef XCA
 #undef X0
 #undef XT0
 #undef XC0
