@@ -219,6 +219,14 @@ class FFTPlan(object):
         in_place = p_in0 == p_out0 or (self._split and p_in1 == p_out1)
         self._ensure_workspace(batch, in_place)
         stream = self._context.get_stream()
+        ws = self._workspace
+        if ws is not None and hasattr(ws, "record_stream"):
+            try:                                   # torch workspace used on a torch stream other than the allocating one
+                import torch
+                if isinstance(stream, torch.cuda.Stream):
+                    ws.record_stream(stream)
+            except ImportError:
+                pass
         _lib.check(self._lib.b2fft_execute(self._handle, p_in0, p_in1, p_out0, p_out1, int(bool(inverse)), batch,
                                            _stream_handle(stream)))
         # the execute kwarg wins over the constructor's setting (plan.py:250-253)
