@@ -29,12 +29,18 @@ CASES = [
     ("d3_16x16x16_dp_split_inv", (16, 16, 16), 2, np.float64, True, True, 1.0),
     ("n16_scale10_fwd", (16,), 1, np.complex64, False, True, 10.0),
     ("n8192_fwd", (8192,), 1, np.complex64, False, True, 1.0),
+    # axes longer than one CTA holds: the four-step path here, the reference's global-kernel chains there
+    ("n32768_fwd", (32768,), 1, np.complex64, False, True, 1.0),
+    ("d2_4096x8_inv", (4096, 8), 1, np.complex64, True, True, 1.0),
 ]
 
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    force = "--force" in sys.argv
     for i, (name, shape, batch, dtype, inverse, normalize, scale) in enumerate(CASES):
+        if os.path.exists(os.path.join(out_dir, name + ".npz")) and not force:
+            continue                                  # committed fixtures are only rewritten with --force
         data = no.make_input(shape, batch, dtype, seed=2000 + i)
         if isinstance(data, tuple):
             re, im = data
