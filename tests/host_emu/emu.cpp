@@ -194,6 +194,74 @@ static void check_blocked(const char* name, long long outer, long long inner, in
     if (!ok) ++g_fail;
 }
 
+// The x-slab exchange pass (pyfft_b200/dist.py _init_xslab): a contiguous-axis pass over the rows
+// {all local z} x {y chunk c} of a z-slab [Zl][Y][X], walked through the two-level outer index of
+// b2fft_plan_set_outer_split, with destination-blocked stores: x-block h of row (z, y) goes to
+// buffer h at [(y*Z + zoff + z)*Xb + xl].  Parameters are set exactly as dist.py / api.cu set them.
+template <class Cfg>
+static void check_xslab_rows(const char* name) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    const int X = Cfg::N, G = 4, Xb = X / G;
+    if (Cfg::W != 1 || X % G) return;
+    const int Zl = 3, Y = 8, C = 2, Yc = Y / C, Z = Zl * G, zoff = Zl;      // "rank 1" of 4: z offset Zl
+    std::mt19937_64 rng(99);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T2> slab((size_t)Zl * Y * X);
+    for (auto& v : slab) { v.x = (T)nd(rng); v.y = (T)nd(rng); }
+    std::vector<std::vector<T2>> xs(G, std::vector<T2>((size_t)Y * Z * Xb));
+    for (auto& b : xs) for (auto& v : b) { v.x = NAN; v.y = NAN; }
+    std::vector<std::vector<T2>> tabs;
+    for (int s = 0; s + 1 < Cfg::S; ++s) tabs.push_back(make_stage_table<T>(Cfg::NS(s), Cfg::R(s)));
+    for (int c = 0; c < C; ++c) {
+        PassParams<T> p{};
+        for (int s = 0; s + 1 < Cfg::S; ++s) p.tw[s] = reinterpret_cast<const T*>(tabs[s].data());
+        p.in0 = reinterpret_cast<const T*>(slab.data() + (size_t)c * Yc * X);
+        p.inner = 1; p.inner_blocks = 1;
+        p.n_tiles = (long long)Yc * Zl;
+        p.out_inner = 1;
+        p.out_blk_log2 = ilog2(Xb);
+        for (int h = 0; h < G; ++h) p.out_blk0[h] = reinterpret_cast<T*>(xs[h].data() + ((size_t)c * Yc * Z + zoff) * Xb);
+        p.outer_div = Yc; p.outer_stride = X; p.in_stride_hi = (long long)Y * X;
+        p.out_outer_stride = (long long)Z * Xb; p.out_stride_hi = Xb;
+        p.scale = 1; p.scale_mode = 0;
+        const long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+        std::vector<T2> smem((size_t)Cfg::COL_SMEM * Cfg::W * Cfg::G + 1);
+        for (long long bid = 0; bid < ctas; ++bid) {
+            std::vector<TileThread<Cfg, false, false>> th(Cfg::THREADS);
+            for (int tid = 0; tid < Cfg::THREADS; ++tid) { th[tid].setup(tid, bid, p); th[tid].load(p); }
+            emu_stages<Cfg, false, false, 0>(th, p, smem);
+            for (auto& t : th) t.template store<true>(p);
+        }
+    }
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(X);
+    for (int z = 0; z < Zl; ++z)
+        for (int y = 0; y < Y; ++y) {
+            for (int x = 0; x < X; ++x) { auto v = slab[((size_t)z * Y + y) * X + x]; line[x] = cld(v.x, v.y); }
+            ref_fft(line);
+            for (int x = 0; x < X; ++x) {
+                const T2 g = xs[x / Xb][((size_t)y * Z + zoff + z) * Xb + x % Xb];
+                double e = (double)std::abs(cld(g.x, g.y) - line[x]);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(line[x]);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    // nothing outside this rank's z range may have been written
+    bool clean = true;
+    for (int h = 0; h < G; ++h)
+        for (int y = 0; y < Y; ++y)
+            for (int z = 0; z < Z; ++z)
+                if (z < zoff || z >= zoff + Zl)
+                    for (int x = 0; x < Xb; ++x) clean = clean && std::isnan((double)xs[h][((size_t)y * Z + z) * Xb + x].x);
+    const double tol = sizeof(T) == 4 ? 3e-6 : 1e-14;
+    const bool ok = max_err / max_mag < tol && clean;
+    std::printf("%-44s x-slab exchange rows (outer split, 4 blocks) err=%.2e %s\n", name, max_err / max_mag, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 template <class Cfg>
 static void check(const char* name, long long outer, long long inner) {
     using T = typename Cfg::T;
@@ -346,6 +414,9 @@ static void check_fourstep(const char* name) {
 #define CHK(T, L, W, G, R0, R1, R2, R3, OUTER, INNER) \
     check<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER); \
     if ((W) > 1 && (L) >= 3) check_blocked<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER, (L) >= 8 ? 8 : 2);
+
+#define CHKXS(T, L, W, G, R0, R1, R2, R3) \
+    check_xslab_rows<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3);
 
 #define CHKF(T, L, W, G, R0, R1, R2, R3) \
     check_fourstep<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3);
