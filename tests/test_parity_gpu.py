@@ -52,7 +52,7 @@ def _run(plan, dev, data, batch, inverse, inplace):
 SHAPES_1D = [(1 << k,) for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13)]
 SHAPES_2D = [(1 << a, 1 << b) for a in (4, 7, 8, 10) for b in (4, 7, 8, 10)]
 SHAPES_3D = [(1 << a, 1 << b, 1 << c) for a in (4, 7) for b in (4, 7) for c in (4, 7)] + [(2, 2, 2), (4, 8, 2), (256, 4, 64)]
-BATCHES = [1, 16, 128]
+BATCHES = [1, 16, 128, 1024, 4096]      # test/test_errors.py:139
 
 
 def _cases():
