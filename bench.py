@@ -41,6 +41,9 @@ WORKLOADS = {
 }
 
 
+CSIZE = {"complex64": 8, "float32": 8, "complex128": 16, "float64": 16}      # bytes per complex element
+
+
 def flops(shape, batch):
     n = int(np.prod(shape))
     return 5.0 * n * math.log2(n) * batch
@@ -113,14 +116,15 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_min_mhz": float(min(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "window": "all timed regions of this run (headline loop, e2e, per-config and slab records)"}
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
@@ -190,28 +194,35 @@ def numpy_scipy_rates(shape, dtype, batch=256):
     return out
 
 
+def workload_config(name, per_gpu_batch):
+    """The `config` object both arms print for a workload (same keys and values, so the driver can match them)."""
+    shape, batch, dtype, passes, desc = WORKLOADS[name]
+    return {"workload": name + ": " + desc, "shape": list(shape), "batch": batch, "per_gpu_batch": per_gpu_batch,
+            "layout": "split" if dtype in ("float32", "float64") else "interleaved", "normalize": True, "out_of_place": True}
+
+
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle/pyfft_port.c; the real
-    pyfft needs Python 2 + Mako + PyCUDA/PyOpenCL and cannot run in this image)."""
+    """--impl reference: the reference's algorithm on the host cores (oracle/pyfft_port.c; the real pyfft needs
+    Python 2 + Mako + PyCUDA/PyOpenCL and cannot run in this image), with all host threads, on the same workload and
+    config as the GPU arm: every step is one out-of-place forward transform of the WHOLE batch.  Rank 0 only: a host
+    CPU baseline does not multiply with --gpus, the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     shape, batch, dtype, passes, desc = WORKLOADS[args.workload]
     from oracle import pyfft_port as pp
-    threads = host_threads()
-    # bounded sample per step: sized from a calibration run so one step is ~1.5 s
     from oracle import numpy_oracle as no
-    cdt = np.complex64 if np.dtype(dtype) in (np.dtype(np.complex64), np.dtype(np.float32)) else np.complex128
-    b = min(batch, max(threads * 4, 64))
-    x = no.make_input(shape, b, cdt, seed=1)
-    pp.execute(x, shape, b, nthreads=threads)
-    t0 = time.perf_counter()
-    pp.execute(x, shape, b, nthreads=threads)
-    dt = time.perf_counter() - t0
-    reps = int(max(1, min(batch // b, 1.5 / max(dt, 1e-6))))
-    if reps > 1:
-        x = np.tile(x, (reps,) + (1,) * (x.ndim - 1))
-        b *= reps
+    threads = host_threads()
+    cdt = np.complex64 if CSIZE[dtype] == 8 else np.complex128
+    size = int(np.prod(shape))
+    # full batch per step when the host can hold it (input + output); otherwise the largest batch that fits 1/4 of RAM
+    try:
+        avail = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 64 << 30
+    b = int(max(1, min(batch, (avail // 4) // (2 * size * np.dtype(cdt).itemsize))))
+    small = no.make_input(shape, min(b, 256), cdt, seed=1)
+    x = np.tile(small, (-(-b // small.shape[0]),) + (1,) * (small.ndim - 1))[:b]
     out = np.empty_like(x)
     for _ in range(args.warmup):
         pp.execute(x, shape, b, out=out, nthreads=threads)
@@ -220,19 +231,296 @@ def run_reference(args):
         pp.execute(x, shape, b, out=out, nthreads=threads)
     el = time.perf_counter() - t0
     rate = flops(shape, b) * args.steps / el / 1e9
-    sample = "each step = batch %d of %s (of the workload's %d), pyfft algorithm restated in C, OpenMP over lines" % (
-        b, "x".join(map(str, shape)), batch)
+    sample = "each step = batch %d of %d of shape %s, pyfft's algorithm restated in C (oracle/pyfft_port.c), OpenMP over lines, %d threads" % (
+        b, batch, "x".join(map(str, shape)), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if cdt == np.complex64 else "f64",
-        "data": "synthetic", "config": {"workload": args.workload + ": " + desc, "device": "host CPU"},
+        "data": "synthetic", "config": workload_config(args.workload, batch),
         "cpu_baseline": {"value": round(rate, 3), "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(rate, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "host-CPU arm: one process on rank 0 whatever --gpus is; its value does not scale with the GPU count",
     }
     print(json.dumps(line), flush=True)
 
+
+# ----------------------------------------------------------------------------------------- per-pass / per-config records
+def _alloc_random(n_el, dtype, dev, gen):
+    """Device-resident standard-normal input: one complex tensor, or a (re, im) pair for the split layouts."""
+    import torch
+    tdt = {"complex64": torch.complex64, "complex128": torch.complex128, "float32": torch.float32, "float64": torch.float64}[dtype]
+    if dtype in ("float32", "float64"):
+        return (torch.randn(n_el, dtype=tdt, device=dev, generator=gen), torch.randn(n_el, dtype=tdt, device=dev, generator=gen))
+    out = torch.empty(n_el, dtype=tdt, device=dev)
+    outr = torch.view_as_real(out)
+    step = max(1, n_el // 16)
+    for i in range(0, n_el, step):                      # in pieces: no second full-size temporary
+        outr[i:i + step].normal_(generator=gen)
+    return out
+
+
+def time_passes(shape, dtype, batch, dev, steps=5, warmup=3, data=None):
+    """Every pass of the plan for `shape` timed on its own: one single-axis plan per axis (the axis mask of
+    b2fft_plan_create_ex), in place on device-resident data, CUDA events on the launching stream.  Axes that need
+    several launches (four-step split) report the launch count.  Returns a list of
+    {axis, variant, launches, ms, gbs, frac} with frac = algorithmic bytes / time / measured HBM peak."""
+    import ctypes
+    import torch
+    from pyfft_b200 import _lib
+    lib = _lib.load()
+    peak, _ = measured_peaks()
+    dims = [1, 1, 1]
+    for i, n in enumerate(reversed(shape)):
+        dims[i] = int(n)
+    split = dtype in ("float32", "float64")
+    prec = _lib.F32 if CSIZE[dtype] == 8 else _lib.F64
+    n_el = int(np.prod(shape)) * batch
+    if data is None:
+        g = torch.Generator(device=dev)
+        g.manual_seed(99)
+        data = _alloc_random(n_el, dtype, dev, g)
+    ptrs = (data[0].data_ptr(), data[1].data_ptr()) if split else (data.data_ptr(), None)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = []
+    for a, name in enumerate("XYZ"):
+        if dims[a] <= 1:
+            continue
+        h = ctypes.c_void_p()
+        _lib.check(lib.b2fft_plan_create_ex(ctypes.byref(h), (ctypes.c_int64 * 3)(*dims), 1 << a, prec,
+                                            _lib.SPLIT if split else _lib.INTERLEAVED, 1, 1.0, 1, dev.index or 0, 0.0, 0))
+        buf = ctypes.create_string_buffer(4096)
+        lib.b2fft_plan_describe(h, buf, len(buf))
+        lines = [l for l in buf.value.decode().splitlines() if l]
+        need = ctypes.c_size_t(0)
+        lib.b2fft_plan_workspace_bytes(h, batch, ctypes.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev) if need.value else None
+        if ws is not None:
+            lib.b2fft_plan_set_workspace(h, ws.data_ptr(), need.value)
+
+        def run():
+            _lib.check(lib.b2fft_execute(h, ptrs[0], ptrs[1], ptrs[0], ptrs[1], 0, batch, stream))
+        for _ in range(warmup):
+            run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        alg = 2.0 * CSIZE[dtype] * n_el                                  # one read + one write of every element
+        out.append({"axis": name, "variant": lines[-1].split("variant=")[1].split()[0] if lines else None,
+                    "launches": len(lines), "ms": round(ms, 4), "gbs": round(alg / ms / 1e6, 1),
+                    "frac": round(alg / ms / 1e6 / peak, 4)})
+        lib.b2fft_plan_destroy(h)
+        del ws
+        for t in (data if split else (data,)):                           # undo the sqrt(N) growth of every unnormalised repeat
+            t.mul_(float(dims[a]) ** (-(warmup + steps) / 2.0))
+    return out
+
+
+def config_record(name, dev, steps=10, warmup=3):
+    """One BASELINE config measured the same way as the headline: out-of-place forward executes of the whole batch,
+    device-resident, plus its per-pass table.  `frac` is the slowest pass's fraction (the dominant kernel)."""
+    import torch
+    from pyfft_b200.cuda import Plan
+    shape, batch, dtype, passes, desc = WORKLOADS[name]
+    split = dtype in ("float32", "float64")
+    n_el = int(np.prod(shape)) * batch
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + sorted(WORKLOADS).index(name))
+    a = _alloc_random(n_el, dtype, dev, g)
+    b = (torch.empty_like(a[0]), torch.empty_like(a[1])) if split else torch.empty_like(a)
+    plan = Plan(shape, dtype=np.dtype(dtype), normalize=True, fast_math=(name != "cfg4"),
+                stream=torch.cuda.current_stream(dev), wait_for_finish=False)
+
+    def step():
+        if split:
+            plan.execute(a[0], a[1], b[0], b[1], batch=batch)
+        else:
+            plan.execute(a, b, batch=batch)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = plan.launch_count
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    launches = (plan.launch_count - l0) // steps
+    del b
+    per_pass = time_passes(shape, dtype, batch, dev, steps=max(3, steps // 2), data=a)
+    peak, _ = measured_peaks()
+    alg = passes * 2.0 * CSIZE[dtype] * n_el
+    rec = {"workload": desc, "ms": round(ms, 5), "gflops": round(flops(shape, batch) / ms / 1e6, 1), "launches_per_step": launches,
+           "algorithmic_passes": passes, "hbm_frac_whole_step": round(alg / ms / 1e6 / peak, 4),
+           "frac": min(q["frac"] for q in per_pass) if per_pass else None, "per_pass": per_pass}
+    if 2 * CSIZE[dtype] * n_el < 2 * 126e6:
+        rec["note"] = "working set fits the 126 MB L2: launch-latency-bound, not graded against the HBM roofline"
+    return rec
+
+
+def slab_record(args, world, rank, dev):
+    """north_star's only collective path, at every N: ONE 2048^3 complex64 forward transform -- N=1: Plan.execute in
+    place, N>1: SlabPlan (z-slabs in, x-slab exchange fused into the X pass over NVLink, x-slabs out) -- plus a 512^3
+    run of the same code path gathered on rank 0 and compared with numpy.fft.fftn, and the single-GPU time measured in
+    the same process so the parallel efficiency t1 / (N * tN) is self-contained."""
+    import torch
+    import torch.distributed as dist
+    from pyfft_b200.cuda import Plan
+    from pyfft_b200.dist import SlabPlan
+    peak, _ = measured_peaks()
+    rec = {"workload": WORKLOADS["cfg5"][4], "n_gpus": world}
+
+    def fill(plan, n, gen):
+        zl = plan.L["Zl"]
+        zs = max(1, zl // 16)
+        for z0 in range(0, zl, zs):
+            z1 = min(zl, z0 + zs)
+            plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, n, n, 2, device=dev, generator=gen)))
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- parity: 512^3 through the same code path, gathered on rank 0, against numpy.fft.fftn (float64)
+    n = args.slab_parity_size
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5000 + rank)
+    try:
+        if world == 1:
+            x = torch.view_as_complex(torch.randn(n, n, n, 2, device=dev, generator=gen))
+            y = x.clone()
+            plan = Plan((n, n, n), dtype=np.complex64, stream=torch.cuda.current_stream(dev), wait_for_finish=False)
+            plan.execute(y)
+            torch.cuda.synchronize(dev)
+            full, got = x.cpu().numpy(), y.cpu().numpy()
+            plan.execute(y, inverse=True)
+            torch.cuda.synchronize(dev)
+            num, den = float(((y - x).abs() ** 2).sum().double().item()), float((x.abs() ** 2).sum().double().item())
+            del x, y, plan
+        else:
+            plan = SlabPlan((n, n, n), dtype=np.complex64, exchange="xslab", chunks=args.slab_chunks)
+            fill(plan, n, gen)
+            x_local = plan.slab.clone()
+            plan.forward()
+            torch.cuda.synchronize(dev)
+            xr, yr = torch.view_as_real(x_local).contiguous(), torch.view_as_real(plan.xslab).contiguous()
+            px = [torch.empty_like(xr) for _ in range(world)] if rank == 0 else None
+            py = [torch.empty_like(yr) for _ in range(world)] if rank == 0 else None
+            dist.gather(xr, px, dst=0)
+            dist.gather(yr, py, dst=0)
+            if rank == 0:
+                full = torch.cat([torch.view_as_complex(t) for t in px], dim=0).cpu().numpy()
+                got = torch.cat([torch.view_as_complex(t).permute(1, 0, 2) for t in py], dim=2).cpu().numpy()   # [Y][Z][Xb] side by side
+            del px, py
+            plan.inverse()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([float(((plan.slab - x_local).abs() ** 2).sum().double().item()),
+                              float((x_local.abs() ** 2).sum().double().item())], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            num, den = t.tolist()
+            plan.close()
+            del plan, x_local
+        parity = {"size": "%d^3" % n, "roundtrip_rel_l2": math.sqrt(num / den), "tolerance": 1e-5 * math.log2(float(n) ** 3),
+                  "oracle": "numpy.fft.fftn in float64 on the gathered input (rank 0)"}
+        if rank == 0:
+            try:
+                import scipy.fft as sf
+                want = sf.fftn(full.astype(np.complex128), workers=host_threads())
+            except Exception:
+                want = np.fft.fftn(full.astype(np.complex128))
+            parity["fwd_rel_l2"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+            del want, full, got
+        rec["parity"] = parity
+    except Exception as exc:
+        rec["parity"] = {"error": str(exc)[:300]}
+    torch.cuda.empty_cache()
+
+    # ---- timing at 2048^3
+    n = args.slab_size
+    size = float(n) ** 3
+    steps = args.slab_steps
+    try:
+        gen.manual_seed(6000 + rank)
+        if world == 1:
+            a = _alloc_random(n ** 3, "complex64", dev, gen)
+            plan = Plan((n, n, n), dtype=np.complex64, stream=torch.cuda.current_stream(dev), wait_for_finish=False)
+            step = lambda: plan.execute(a)
+            rec["plan"] = plan.passes
+        else:
+            plan = SlabPlan((n, n, n), dtype=np.complex64, exchange="xslab", chunks=args.slab_chunks)
+            fill(plan, n, gen)
+            step = plan.forward
+            rec["plan"] = plan.describe() if hasattr(plan, "describe") else "x-slab"
+        for _ in range(3):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = plan.launch_count
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = allmax(e0.elapsed_time(e1) / steps)
+        rec.update({"ms": round(ms, 3), "steps": steps, "gflops": round(5.0 * size * math.log2(size) / ms / 1e6, 1),
+                    "gpu_launches_per_step": (plan.launch_count - l0) // steps})
+        per_gpu_alg = 3 * 2.0 * 8 * size / world                          # P = 3 passes over this rank's share
+        rec["hbm_frac"] = round(per_gpu_alg / ms / 1e6 / peak, 4)
+        if world > 1:
+            sent = 8.0 * size / world * (world - 1) / world
+            rec["nvlink"] = {"sent_bytes_per_gpu": int(sent), "achieved_gbs": round(sent / ms / 1e6, 1),
+                             "frac_of_770": round(sent / ms / 1e6 / 770.0, 4),
+                             "note": "bytes each GPU sends over NVLink / WHOLE step time (local passes included)"}
+            plan.close()
+        else:
+            rec["per_pass"] = time_passes((n, n, n), "complex64", 1, dev, steps=3, warmup=1, data=a)
+            rec["frac"] = min(q["frac"] for q in rec["per_pass"])
+            del a
+        del plan
+        torch.cuda.empty_cache()
+        # ---- the single-GPU time beside it (rank 0 runs the ordinary in-place Plan on a full 2048^3 array)
+        if world > 1:
+            t1 = 0.0
+            if rank == 0:
+                a = _alloc_random(n ** 3, "complex64", dev, gen)
+                p1 = Plan((n, n, n), dtype=np.complex64, stream=torch.cuda.current_stream(dev), wait_for_finish=False)
+                for _ in range(2):
+                    p1.execute(a)
+                torch.cuda.synchronize(dev)
+                e0.record()
+                for _ in range(steps):
+                    p1.execute(a)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                t1 = e0.elapsed_time(e1) / steps
+                del a, p1
+                torch.cuda.empty_cache()
+            t1 = allmax(t1)
+            rec["t1_ms"] = round(t1, 3)
+            rec["parallel_efficiency"] = round(t1 / (world * ms), 4)
+        else:
+            rec["t1_ms"] = rec["ms"]
+            rec["parallel_efficiency"] = 1.0
+    except Exception as exc:
+        rec["error"] = str(exc)[:300]
+    return rec
 
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_slab(args):
@@ -395,7 +683,6 @@ def run_b2fft(args):
         step()
     ev1.record()
     barrier()
-    clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = plan.launch_count - launches0
     if world > 1:
@@ -409,12 +696,22 @@ def run_b2fft(args):
     peak, peak_src = measured_peaks()
     compulsory = 2.0 * csize * n_el                         # read every input once + write every output once
     alg_bytes_per_launch = compulsory                        # every pass is one full read + write of the data
-    per_launch_ms = ms_per_step / passes                     # passes launches per step, equal bytes each
+    # the dominant kernel = the slowest pass.  One-pass plans: the step IS the kernel (events around the timed loop);
+    # multi-pass plans: every pass is timed on its own (single-axis plans on the same data) and the slowest one is reported
+    per_pass = None
+    if passes > 1 and not split:
+        per_pass = time_passes(shape, dtype, batch, dev, steps=max(3, min(args.steps, 10)), data=a)
+    if per_pass:
+        worst = min(per_pass, key=lambda q: q["frac"])
+        per_launch_ms, dominant = worst["ms"], "%s pass (%s)" % (worst["axis"], worst["variant"])
+    else:
+        per_launch_ms, dominant = ms_per_step / passes, "the single pass" if passes == 1 else "average over the passes"
     achieved = alg_bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
-                "launches_per_step": passes,
+                "launches_per_step": passes, "dominant_kernel": dominant, "per_pass": per_pass,
+                "whole_step_frac": round(passes * alg_bytes_per_launch / (ms_per_step * 1e-3) / 1e9 / peak, 4),
                 "compulsory_fraction": round(compulsory / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
 
     # ---- end to end: pinned host buffers, H2D + execute + D2H inside the timed region
@@ -471,17 +768,42 @@ def run_b2fft(args):
         except Exception as exc:
             cpu_baseline = {"value": None, "error": str(exc)[:200]}
 
+    # ---- every other BASELINE config, measured in this same run (rank 0's GPU; the other ranks wait)
+    configs = None
+    plan_desc = plan.passes
+    if args.workload == "cfg2" and not args.no_configs:
+        del plan
+        if split:
+            del a_re, a_im, b_re, b_im
+        else:
+            del a, b
+        torch.cuda.empty_cache()
+        if rank == 0:
+            configs = {}
+            for name in ("cfg1", "cfg2s", "cfg3", "cfg4"):
+                try:
+                    configs[name] = config_record(name, dev)
+                except Exception as exc:
+                    configs[name] = {"error": str(exc)[:200]}
+                torch.cuda.empty_cache()
+        barrier()
+    # ---- the slab-decomposed 2048^3 transform (the path with a collective), at every N
+    slab = None
+    if args.workload == "cfg2" and not args.no_slab:
+        slab = slab_record(args, world, rank, dev)
+    clocks = sampler.stop()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if csize == 8 else "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc, "per_gpu_batch": batch, "out_of_place": True,
-                       "l2": "inputs+outputs (%.0f MiB) exceed the 126 MB L2; no flush needed" % (2 * csize * n_el / 2 ** 20)
-                       if 2 * csize * n_el > 2 * 126e6 else "working set fits L2 (launch-bound config)",
-                       "plan": plan.passes, "parallelism": "batch sharded over %d GPU(s), no collective" % world},
+            "config": workload_config(args.workload, batch),
+            "run": {"l2": "inputs+outputs (%.0f MiB) exceed the 126 MB L2; no flush needed" % (2 * csize * n_el / 2 ** 20)
+                    if 2 * csize * n_el > 2 * 126e6 else "working set fits L2 (launch-bound config)",
+                    "plan": plan_desc, "parallelism": "batch sharded over %d GPU(s), no collective" % world},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "configs": configs, "slab": slab,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -497,6 +819,12 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1/cfg2s/cfg3/cfg4 sub-records")
+    ap.add_argument("--no-slab", action="store_true", help="skip the 2048^3 slab record")
+    ap.add_argument("--slab-size", type=int, default=2048)
+    ap.add_argument("--slab-parity-size", type=int, default=512)
+    ap.add_argument("--slab-steps", type=int, default=5)
+    ap.add_argument("--slab-chunks", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

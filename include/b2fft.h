@@ -106,6 +106,15 @@ B2FFT_API int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, 
 B2FFT_API int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk0, void* const* blk1,
                                  int64_t out_inner, int64_t out_outer_stride);
 
+/* Mirror image of b2fft_plan_set_output_blocks for the inverse slab transform: the plan (which must consist of one
+ * contiguous-axis pass, interleaved layout) LOADS input index n of every line from block h = n / (n_axis/nblocks),
+ *     blk0[h][ line_offset + n % (n_axis/nblocks) ]
+ * with line_offset given by the two-level outer index of b2fft_plan_set_outer_split (input strides).  Block
+ * pointers may be peer GPUs' buffers mapped over NVLink: the pass then pulls its lines together from the ranks
+ * that hold the pieces and no separate exchange step exists.  in0 of b2fft_execute is ignored.  nblocks = 0 restores
+ * plain input. */
+B2FFT_API int b2fft_plan_set_input_blocks(b2fft_plan* plan, int nblocks, const void* const* blk0);
+
 /* Slab exchange passes only.  Gives the plan's LAST pass a two-level outer index: its outer index o
  * (row number for a contiguous-axis pass, [n][inner] block number for a strided pass) is split as
  * (hi, lo) = (o / outer_div, o % outer_div) and the line/tile starts at
@@ -132,6 +141,42 @@ B2FFT_API int b2fft_ipc_import(const unsigned char handle[64], int device, void*
 B2FFT_API int b2fft_ipc_release(void* dptr);
 
 B2FFT_API int b2fft_plan_destroy(b2fft_plan* plan);
+
+/* ---- slab-decomposed 3-D transform over several GPUs (no reference counterpart: the
+ * reference runs every kernel of a plan on one stream of one device, pyfft/plan.py:204-245).
+ *
+ * One b2fft_slab_plan per rank (= per GPU; one process per GPU, or one process driving several devices).  Rank g
+ * owns z in [g*Z/G, (g+1)*Z/G) of the (Z, Y, X) array as the z-slab [Z/G][Y][X]; b2fft_slab_forward leaves rank h
+ * with x in [h*X/G, (h+1)*X/G) as the x-slab [Y][Z][X/G] (one exchange, result stays distributed);
+ * b2fft_slab_inverse goes back.  The exchange is fused into an FFT pass over peer-mapped memory (forward: the X
+ * pass stores its rows as G contiguous pieces into the ranks' x-slabs; inverse: the X pass pulls them), ranks
+ * synchronise through epoch words in peer-mapped memory, and the passes of neighbouring chunks overlap the NVLink
+ * traffic on plan-owned streams -- see pyfft_b200/csrc/slab.cu.  Scaling follows pyfft/kernel.py:23-37 with
+ * size = X*Y*Z.  Interleaved layout only.
+ *
+ *   y_chunks / z_chunks      pipeline depth of the exchange (0 = defaults 8 / 1)
+ *   exchange_ctas_per_sm     grid cap of the NVLink-bound X pass (0 = none), see b2fft_plan_set_exchange_ctas
+ * The caller provides the buffers (b2fft_slab_plan_sizes; e.g. b2fft_mem_alloc + b2fft_ipc_export/import between
+ * processes, or plain cudaMalloc + cudaDeviceEnablePeerAccess inside one process) and passes, for EVERY rank r, the
+ * address under which rank r's x-slab and flag buffer are reachable from this plan's device.  Flag buffers must be
+ * attached before any rank calls forward/inverse.  All ranks must issue the same sequence of forward/inverse calls.
+ * Both calls are asynchronous on `cuda_stream`. */
+typedef struct b2fft_slab_plan b2fft_slab_plan;
+B2FFT_API int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int precision, int normalize,
+                                     double scale, int fast_math, int device, int rank, int nranks, int y_chunks,
+                                     int z_chunks, int exchange_ctas_per_sm);
+B2FFT_API int b2fft_slab_plan_sizes(const b2fft_slab_plan* plan, size_t* slab_bytes, size_t* xslab_bytes, size_t* flag_bytes);
+/* {Z/G, X/G, y_chunks, z_chunks, Y/y_chunks, (Z/G)/z_chunks, G, rank} */
+B2FFT_API int b2fft_slab_plan_geometry(const b2fft_slab_plan* plan, int64_t out[8]);
+B2FFT_API int b2fft_slab_plan_attach(b2fft_slab_plan* plan, void* slab, void* const* xslab_of_rank, void* const* flags_of_rank);
+B2FFT_API int b2fft_slab_forward(b2fft_slab_plan* plan, void* cuda_stream);
+B2FFT_API int b2fft_slab_inverse(b2fft_slab_plan* plan, void* cuda_stream);
+/* 0 = healthy; non-zero = a cross-rank wait timed out (a peer never signalled); synchronises the device */
+B2FFT_API int b2fft_slab_plan_status(b2fft_slab_plan* plan, int* out);
+B2FFT_API int64_t b2fft_slab_plan_launch_count(const b2fft_slab_plan* plan);
+B2FFT_API int b2fft_slab_plan_describe(const b2fft_slab_plan* plan, char* buf, size_t buflen);
+B2FFT_API int b2fft_slab_plan_destroy(b2fft_slab_plan* plan);
+B2FFT_API const char* b2fft_slab_last_error(void);
 
 /* Replaces Context.wait (pyfft/cuda.py:98-101): blocks until the stream has drained.  Only
  * needed by callers that hold a raw cudaStream_t; torch callers synchronise their own stream. */

@@ -32,6 +32,18 @@ SIGNATURES = {
     "b2fft_execute": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "b2fft_plan_destroy": (_i, [_vp]),
     "b2fft_plan_set_output_blocks": (_i, [_vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _i64]),
+    "b2fft_plan_set_input_blocks": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
+    "b2fft_slab_plan_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _i, _d, _i, _i, _i, _i, _i, _i, _i]),
+    "b2fft_slab_plan_sizes": (_i, [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "b2fft_slab_plan_geometry": (_i, [_vp, ctypes.POINTER(_i64)]),
+    "b2fft_slab_plan_attach": (_i, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "b2fft_slab_forward": (_i, [_vp, _vp]),
+    "b2fft_slab_inverse": (_i, [_vp, _vp]),
+    "b2fft_slab_plan_status": (_i, [_vp, ctypes.POINTER(_i)]),
+    "b2fft_slab_plan_launch_count": (_i64, [_vp]),
+    "b2fft_slab_plan_describe": (_i, [_vp, ctypes.c_char_p, _sz]),
+    "b2fft_slab_plan_destroy": (_i, [_vp]),
+    "b2fft_slab_last_error": (ctypes.c_char_p, []),
     "b2fft_plan_set_outer_split": (_i, [_vp, _i64, _i64, _i64, _i64, _i64]),
     "b2fft_plan_set_exchange_ctas": (_i, [_vp, _i]),
     "b2fft_mem_alloc": (_i, [_sz, _i, ctypes.POINTER(_vp)]),

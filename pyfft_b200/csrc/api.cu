@@ -60,9 +60,11 @@ struct Registry {
         b2::register_f32_col(v);
         b2::register_f64_row(v);
         b2::register_f64_col(v);
+        b2::register_fused(v);
         n_default = v.size();
         b2::register_exp(v);   // tuning candidates, never picked by default (listed last)
         b2::register_exp2(v);
+        b2::register_fused_exp(v);
         prepared.assign(v.size(), false);
         if (const char* e = getenv("B2FFT_PREFER")) set_preferred(e);
     }
@@ -86,11 +88,22 @@ struct Registry {
         auto ok = [&](const KernelVariant& k) {
             if (k.prec != prec || k.log2n != log2n) return false;
             if (contiguous) return k.W == 1;
+            if (k.kind == 3 && split) return false;          // fused two-step kernels: interleaved layout only
             return (k.W > 1 && k.kind != 1) ? (inner % k.W == 0) : false;
         };
         for (const auto& name : preferred)
             for (size_t i = 0; i < v.size(); ++i)
                 if (name == v[i].name && ok(v[i])) return (int)i;
+        // Rows of the transformed axis >= 256 KiB apart (Z passes of large 3-D arrays): the memory system serves ~45 G row
+        // pieces per second whatever their size up to 128 bytes (profiles/r02_strided_copy_bw.txt), so only 128-byte pieces
+        // get near the peak -- the fused two-step kernels (N >= 1024, interleaved).  Measured on 2048^3 / 1024^3 Z passes:
+        // 3412 / 4121 GB/s against 2772 / 3707 GB/s for the widest single-pass tile (profiles/r02_fused2.md).  At smaller
+        // pitch the single-pass TMA-staged tiles are faster (their neighbours share DRAM pages) and stay the default.
+        static const int fused_mode = [] { const char* e = getenv("B2FFT_FUSED2"); return e ? atoi(e) : 1; }();   // 0 never, 1 large pitch, 2 always
+        const long long pitch0 = inner * (prec ? 16 : 8);
+        if (!contiguous && fused_mode > 0 && (fused_mode > 1 || pitch0 >= (256 << 10)))
+            for (size_t i = 0; i < n_default; ++i)
+                if (v[i].kind == 3 && ok(v[i])) return (int)i;
         const long long pitch = inner * (prec ? 16 : 8);
         if (!contiguous && pitch >= (256 << 10)) {
             int best = -1;
@@ -102,7 +115,7 @@ struct Registry {
             for (size_t i = 0; i < n_default; ++i)
                 if (ok(v[i]) && v[i].kind == 1) return (int)i;
         for (size_t i = 0; i < v.size(); ++i)
-            if (ok(v[i])) return (int)i;
+            if (ok(v[i]) && v[i].kind != 3) return (int)i;
         if (!contiguous) return pick_direct_w1(prec, log2n);   // narrow inner dimension: one column per tile
         return -1;
     }
@@ -137,7 +150,7 @@ struct Registry {
     int max_log2(int prec, bool contiguous) {
         int m = 0;
         for (size_t i = 0; i < n_default; ++i)
-            if (v[i].prec == prec && (contiguous ? v[i].W == 1 : v[i].W > 1) && v[i].log2n > m) m = v[i].log2n;
+            if (v[i].prec == prec && v[i].kind != 3 && (contiguous ? v[i].W == 1 : v[i].W > 1) && v[i].log2n > m) m = v[i].log2n;
         return m;
     }
     // first plain (non-TMA) W = 1 variant: strided fallback, and the fallback for unaligned pointers
@@ -239,6 +252,13 @@ struct DeviceGuard {
     }
 };
 
+// plans without any pass (every transformed axis has length 1): out = in * f (mode 1) or in / f (mode 2)
+template <typename T>
+__global__ void scale_copy_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n, T f, int mode) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = mode == 1 ? in[i] * f : in[i] / f;
+}
+
 bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 int ilog2ll(long long v) {
     int l = 0;
@@ -255,6 +275,7 @@ struct Pass {
     long long inner;       // element stride of the transformed axis
     const void* tw[3];
     const void* tw_fb[3];  // twiddle tables of the fallback variant (its radices may differ)
+    const void* tw_b[3];   // fused two-step variants: stage tables of step B (tw = step A, fs_t1/fs_t2 = inter-step twiddle)
     // four-step "A" pass (transposing): this pass is the length-n = N1 part of an axis of length
     // fs_total = N1*N2 whose elements are inner0 apart; it stores [n2][k1][inner0]
     bool transposing;
@@ -279,23 +300,48 @@ struct b2fft_plan {
     void* blk0[B2_MAX_BLOCKS] = {};
     void* blk1[B2_MAX_BLOCKS] = {};
     long long blk_out_inner = 0, blk_out_outer_stride = 0;
+    // source-blocked input of the first pass (b2fft_plan_set_input_blocks)
+    int in_nblocks = 0;
+    const void* in_blk[B2_MAX_BLOCKS] = {};
     // two-level outer index of the last pass (b2fft_plan_set_outer_split)
     int exchange_max_ctas = 0;   // grid cap of the last pass (b2fft_plan_set_exchange_ctas)
     long long split_div = 0, split_in_lo = 0, split_in_hi = 0, split_out_lo = 0, split_out_hi = 0;
     std::atomic<long long> launches{0};
+    long long fused_slots_for(long long slot_elems) const {
+        return slot_elems > 0 ? (long long)(fused_scratch_bytes / ((size_t)slot_elems * (prec ? 16 : 8))) : 0;
+    }
     int n_transposing = 0;   // four-step "A" passes (cannot run in place)
+    // scratch of the fused two-step strided kernels: one super-tile slot per resident CTA, plan-owned, L2-resident in use
+    void* fused_scratch = nullptr;
+    size_t fused_scratch_bytes = 0;
     bool dry = false;        // b2fft_plan_preview: plan the passes only, no device work
 };
 
 namespace {
 
-int stage_tables(b2fft_plan* pl, const KernelVariant& kv, long long n, const void** tw) {
+int stage_tables_r(b2fft_plan* pl, const int* radix, int S, long long n, const void** tw) {
     if (pl->dry) return 0;
     int NS = (int)n;
-    for (int s = 0; s + 1 < kv.S; ++s) {
-        int rc = twiddles().get(pl->device, pl->prec, NS, kv.radix[s], &tw[s]);
+    for (int s = 0; s + 1 < S; ++s) {
+        int rc = twiddles().get(pl->device, pl->prec, NS, radix[s], &tw[s]);
         if (rc) return rc;
-        NS /= kv.radix[s];
+        NS /= radix[s];
+    }
+    return 0;
+}
+int stage_tables(b2fft_plan* pl, const KernelVariant& kv, long long n, const void** tw) {
+    return stage_tables_r(pl, kv.radix, kv.S, kv.kind == 3 ? (1LL << kv.log2n1) : n, tw);
+}
+// fused two-step variant: step B's stage tables and the inter-step twiddle tables w_N^(k1*n2) (same factorisation
+// into two small tables as the four-step "A" passes, see FsTwiddleCache)
+int fused_tables(b2fft_plan* pl, const KernelVariant& kv, Pass& p) {
+    if (pl->dry) return 0;
+    const long long n = 1LL << kv.log2n, n1 = 1LL << kv.log2n1, n2 = n >> kv.log2n1;
+    int rc = stage_tables_r(pl, kv.radix_b, kv.S_b, n2, p.tw_b);
+    if (rc) return rc;
+    for (int which = 1; which <= 2; ++which) {
+        rc = fs_twiddles().get(pl->device, pl->prec, which, n, n2, (int)(n1 / kv.E), kv.E, which == 1 ? &p.fs_t1 : &p.fs_t2);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -314,6 +360,7 @@ int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
     Pass p{};
     p.variant = vi;
     p.fallback = kv.kind == 0 ? vi : kv.kind == 1 ? reg.pick_direct_w1(pl->prec, lg) : reg.pick_direct_col(pl->prec, lg, inner, fs);
+    if (kv.kind == 3 && fs) return fail(B2FFT_E_UNSUPPORTED, "fused variant picked for a transposing pass");
     if (p.fallback < 0) return fail(B2FFT_E_UNSUPPORTED, "no fallback kernel for axis %c", "xyz"[axis]);
     p.axis = axis;
     p.log2n = lg;
@@ -323,6 +370,16 @@ int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
     if (rc) return rc;
     cudaError_t e = pl->dry ? cudaSuccess : reg.prepare(vi);
     if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+    if (kv.kind == 3) {
+        rc = fused_tables(pl, kv, p);
+        if (rc) return rc;
+        if (!pl->dry) {
+            const long long slots = kv.grid_slots();
+            if (slots <= 0) return fail(B2FFT_E_CUDA, "occupancy query failed for %s", kv.name);
+            const size_t bytes = (size_t)slots * (size_t)kv.slot_elems * (pl->prec ? 16 : 8);
+            if (bytes > pl->fused_scratch_bytes) pl->fused_scratch_bytes = bytes;
+        }
+    }
     const KernelVariant& fb = reg.v[p.fallback];
     if (p.fallback != vi) {
         rc = stage_tables(pl, fb, n, p.tw_fb);
@@ -393,9 +450,12 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
             (registry().v[vi].kind == 2 && (pitch % 16 != 0 || outer_count > 0x7fffffffLL)))
             vi = ps.fallback;
     }
+    const bool in_blocked = pl->in_nblocks > 0 && &ps == &pl->passes.front();
+    if (in_blocked) vi = ps.fallback;                                    // source-blocked loads live in the plain kernels
     const bool outer_split = last && pl->split_div > 0;
     if (outer_split && registry().v[vi].kind != 0) vi = ps.fallback;   // TMA staging assumes a dense outer index
     if (last && pl->nblocks > 0 && !registry().v[vi].blk) vi = ps.fallback;
+    if (registry().v[vi].kind == 3 && (!pl->fused_scratch || (last && pl->exchange_max_ctas > 0))) vi = ps.fallback;
     const KernelVariant& kv = registry().v[vi];
     b2::PassParams<T> p{};
     if (split && inverse) {   // IDFT(z) = swap(DFT(swap(z))): swap the planes instead of the registers
@@ -411,6 +471,19 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
     p.out_inner = p.inner;
     p.out_outer_stride = p.outer_stride;
     p.out_blk_log2 = -1;
+    p.in_blk_log2 = -1;
+    if (in_blocked) {
+        if (kv.W != 1 || kv.kind != 0 || split) return fail(B2FFT_E_UNSUPPORTED, "source-blocked loads need a plain contiguous-axis kernel");
+        p.in_blk_log2 = ilog2ll(ps.n / pl->in_nblocks);
+        for (int h = 0; h < pl->in_nblocks; ++h) p.in_blk[h] = (const T*)pl->in_blk[h];
+    }
+    if (kv.kind == 3) {
+        for (int s = 0; s < 3; ++s) p.tw_b[s] = (const T*)ps.tw_b[s];
+        p.fs_t1 = (const T*)ps.fs_t1;
+        p.fs_t2 = (const T*)ps.fs_t2;
+        p.scratch = (T*)pl->fused_scratch;
+        p.scratch_slots = pl->fused_slots_for(kv.slot_elems);
+    }
     if (ps.transposing) {
         p.out_inner = ps.inner0;
         p.fs_log2_inner = ilog2ll(ps.inner0);
@@ -507,6 +580,19 @@ int b2fft_plan_create_ex(b2fft_plan** out, const int64_t dims_xyz[3], int axes_m
     pl->apply_scale = apply_scale ? 1 : 0;
     int rc = build_passes(pl);
     if (rc) { delete pl; return rc; }
+    if (pl->fused_scratch_bytes) {
+        cudaError_t e = cudaMalloc(&pl->fused_scratch, pl->fused_scratch_bytes);
+        if (e != cudaSuccess) {
+            delete pl;
+            return fail(B2FFT_E_CUDA, "cudaMalloc of %zu scratch bytes: %s", pl->fused_scratch_bytes, cudaGetErrorString(e));
+        }
+    }
+    // the table uploads above are cudaMemcpy calls from pageable memory, ordered on the legacy default stream only:
+    // drain it so that an execute on a non-blocking stream right after plan creation cannot overtake them
+    if (cudaError_t e = cudaStreamSynchronize(cudaStreamLegacy); e != cudaSuccess) {
+        b2fft_plan_destroy(pl);
+        return fail(B2FFT_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    }
     *out = pl;
     return B2FFT_OK;
 }
@@ -567,12 +653,24 @@ int b2fft_execute(b2fft_plan* plan, const void* in0, const void* in1, void* out0
     if (guard.err != cudaSuccess) return fail(B2FFT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
     cudaStream_t stream = (cudaStream_t)cuda_stream;
 
-    if (plan->passes.empty()) {   // all axes of length 1 (or masked out): identity (times the scale), as a copy
-        if (in0 != out0 || (split && in1 != out1)) {
-            const size_t esz = (plan->prec ? 8 : 4) * (split ? 1 : 2);
-            const size_t bytes = (size_t)(plan->x * plan->y * plan->z) * (size_t)batch * esz;
-            CUDA_TRY(cudaMemcpyAsync(out0, in0, bytes, cudaMemcpyDeviceToDevice, stream));
-            if (split) CUDA_TRY(cudaMemcpyAsync(out1, in1, bytes, cudaMemcpyDeviceToDevice, stream));
+    if (plan->passes.empty()) {   // all axes of length 1 (or masked out): the identity times the scale factor
+        const size_t reals = (size_t)(plan->x * plan->y * plan->z) * (size_t)batch * (split ? 1 : 2);
+        double coeff = 1.0;   // pyfft/kernel.py:23-37, as in launch_pass()
+        if (plan->apply_scale) coeff = inverse ? (plan->normalize ? plan->norm_size : 1.0) * plan->scale : 1.0 / plan->scale;
+        const int mode = coeff == 1.0 ? 0 : plan->fast_math ? 1 : 2;
+        const double f = mode == 1 ? 1.0 / coeff : coeff;
+        for (int pl = 0; pl < (split ? 2 : 1); ++pl) {
+            const void* src = pl ? in1 : in0;
+            void* dst = pl ? out1 : out0;
+            if (mode == 0) {
+                if (src != dst) CUDA_TRY(cudaMemcpyAsync(dst, src, reals * (plan->prec ? 8 : 4), cudaMemcpyDeviceToDevice, stream));
+                continue;
+            }
+            const unsigned blocks = (unsigned)((reals + 255) / 256 > 65535 * 16 ? 65535 * 16 : (reals + 255) / 256);
+            if (plan->prec) scale_copy_kernel<double><<<blocks, 256, 0, stream>>>((const double*)src, (double*)dst, reals, f, mode);
+            else scale_copy_kernel<float><<<blocks, 256, 0, stream>>>((const float*)src, (float*)dst, reals, (float)f, mode);
+            CUDA_TRY(cudaGetLastError());
+            plan->launches.fetch_add(1, std::memory_order_relaxed);
         }
         return B2FFT_OK;
     }
@@ -702,6 +800,25 @@ int b2fft_plan_set_output_blocks(b2fft_plan* plan, int nblocks, void* const* blk
     return B2FFT_OK;
 }
 
+int b2fft_plan_set_input_blocks(b2fft_plan* plan, int nblocks, const void* const* blk0) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (nblocks == 0) { plan->in_nblocks = 0; return B2FFT_OK; }
+    if (nblocks < 0 || nblocks > B2_MAX_BLOCKS || (nblocks & (nblocks - 1)))
+        return fail(B2FFT_E_INVALID, "nblocks must be a power of two <= %d", B2_MAX_BLOCKS);
+    if (plan->passes.size() != 1 || plan->passes[0].axis != 0 || plan->passes[0].transposing)
+        return fail(B2FFT_E_UNSUPPORTED, "source-blocked loads need a plan with exactly one pass, over the contiguous axis");
+    if (plan->layout == B2FFT_SPLIT) return fail(B2FFT_E_UNSUPPORTED, "source-blocked loads handle the interleaved layout");
+    if (!blk0) return fail(B2FFT_E_INVALID, "null block pointer table");
+    if (plan->passes[0].n % nblocks) return fail(B2FFT_E_INVALID, "axis length %lld not divisible by %d", plan->passes[0].n, nblocks);
+    const size_t align = plan->prec ? 16 : 8;
+    for (int h = 0; h < nblocks; ++h) {
+        if (!blk0[h] || ((uintptr_t)blk0[h] % align)) return fail(B2FFT_E_INVALID, "bad block pointer %d", h);
+        plan->in_blk[h] = blk0[h];
+    }
+    plan->in_nblocks = nblocks;
+    return B2FFT_OK;
+}
+
 int b2fft_plan_set_outer_split(b2fft_plan* plan, int64_t outer_div, int64_t in_stride_lo, int64_t in_stride_hi,
                                int64_t out_stride_lo, int64_t out_stride_hi) {
     if (!plan) return fail(B2FFT_E_INVALID, "null plan");
@@ -761,6 +878,11 @@ int b2fft_ipc_release(void* dptr) {
 }
 
 int b2fft_plan_destroy(b2fft_plan* plan) {
+    if (plan && plan->fused_scratch) {
+        DeviceGuard guard(plan->device);
+        cudaFree(plan->fused_scratch);
+        plan->fused_scratch = nullptr;
+    }
     delete plan;
     return B2FFT_OK;
 }
@@ -835,14 +957,26 @@ int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, v
     tmp.prec = k.prec; tmp.layout = split ? B2FFT_SPLIT : B2FFT_INTERLEAVED; tmp.apply_scale = 0; tmp.device = device;
     Pass p{};
     p.variant = index; p.fallback = index; p.log2n = k.log2n; p.n = 1LL << k.log2n; p.inner = inner;
-    int NS = (int)p.n;
-    for (int s = 0; s + 1 < k.S; ++s) {
-        int rc = twiddles().get(device, k.prec, NS, k.radix[s], &p.tw[s]);
-        if (rc) return rc;
-        NS /= k.radix[s];
-    }
+    int rc0 = stage_tables(&tmp, k, p.n, p.tw);
+    if (rc0) return rc0;
     cudaError_t e = reg.prepare(index);
     if (e != cudaSuccess) return fail(B2FFT_E_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+    if (k.kind == 3) {   // tuning runs share one scratch buffer per device (never freed; single stream at a time)
+        rc0 = fused_tables(&tmp, k, p);
+        if (rc0) return rc0;
+        static std::mutex mu;
+        static std::map<int, std::pair<void*, size_t>> pool;
+        std::lock_guard<std::mutex> lk(mu);
+        const size_t need = (size_t)k.grid_slots() * (size_t)k.slot_elems * (k.prec ? 16 : 8);
+        auto& ent = pool[device];
+        if (ent.second < need) {
+            if (ent.first) cudaFree(ent.first);
+            CUDA_TRY(cudaMalloc(&ent.first, need));
+            ent.second = need;
+        }
+        tmp.fused_scratch = ent.first;
+        tmp.fused_scratch_bytes = ent.second;
+    }
     const long long inner_blocks = inner / k.W;
     if (n_tiles % inner_blocks != 0) return fail(B2FFT_E_INVALID, "n_tiles must be a multiple of inner/W");
     const long long outer = n_tiles / inner_blocks;

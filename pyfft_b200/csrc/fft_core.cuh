@@ -232,6 +232,10 @@ struct PassParams {
     int out_blk_log2;        // < 0: plain stores to out0/out1
     T* out_blk0[B2_MAX_BLOCKS];
     T* out_blk1[B2_MAX_BLOCKS];
+    // source-blocked loads (inverse of the above, contiguous-axis passes only): input index n comes from block
+    // h = n >> in_blk_log2 at in-block position n & (2^in_blk_log2 - 1) of in_blk[h], local or peer (NVLink) memory
+    int in_blk_log2;         // < 0 (or 0 with in_blk[0] == nullptr): plain loads from in0/in1
+    const T* in_blk[B2_MAX_BLOCKS];
     // two-level outer index (slab exchange passes): when outer_div > 0 the outer index o is split as
     // (o_hi, o_lo) = (o / outer_div, o % outer_div) and the tile starts at
     //   in:  o_hi*in_stride_hi  + o_lo*outer_stride       out: o_hi*out_stride_hi + o_lo*out_outer_stride
@@ -251,6 +255,13 @@ struct PassParams {
     long long fs_col_stride;  // N1 * inner0: output element stride between consecutive n2
     const T* fs_t1;           // vec2<T> [TPC][N2]: w_N^(t*n2)
     const T* fs_t2;           // vec2<T> [E][N2]:   w_N^(TPC*c*n2)
+    // fused two-step strided kernel (kernels.cuh fused2_fft_kernel): stage tables of step B and the scratch
+    // buffer that holds the intermediate [n2][k1][W] of one super-tile per resident CTA (stays in L2)
+    const T* tw_b[3];
+    T* scratch;
+    long long scratch_slots;  // number of super-tile slots the scratch buffer holds
+    int fused_flags;          // bit 0: discard scratch lines after step B read them, 1: prefetch the next super-tile into L2,
+                              // 2: evict-first policy on the DRAM streams, 3: evict-last policy on the scratch slot
 };
 
 // ------------------------------------------------------------------ compile-time plan
@@ -320,6 +331,40 @@ B2_HD cpx<T> ld_stream_c(const vec2<T>* p) {
     return cmake<T>(p->x, p->y);
 #endif
 }
+// ... the same with an L2 cache policy (createpolicy): the fused two-step kernel streams its DRAM traffic through
+// L2 as evict-first and keeps its scratch slot evict-last
+template <typename T>
+B2_HD cpx<T> ld_stream_c_pol(const vec2<T>* p, unsigned long long pol) {
+#if defined(__CUDA_ARCH__)
+    cpx<T> c;
+    if constexpr (is_packed<T>::value) {
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(c.v) : "l"(p), "l"(pol));
+    } else if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(c.x), "=f"(c.y) : "l"(p), "l"(pol));
+    } else {
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(c.x), "=d"(c.y) : "l"(p), "l"(pol));
+    }
+    return c;
+#else
+    (void)pol;
+    return cmake<T>(p->x, p->y);
+#endif
+}
+template <typename T>
+B2_HD void st_c_pol(vec2<T>* p, const cpx<T>& c, unsigned long long pol) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (is_packed<T>::value) {
+        asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(c.v), "l"(pol) : "memory");
+    } else if constexpr (sizeof(T) == 4) {
+        asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(c.x), "f"(c.y), "l"(pol) : "memory");
+    } else {
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(c.x), "d"(c.y), "l"(pol) : "memory");
+    }
+#else
+    (void)pol;
+    vec2<T> v; v.x = c.x; v.y = c.y; *p = v;
+#endif
+}
 template <typename T>
 B2_HD T ld_stream1(const T* p) {
 #if defined(__CUDA_ARCH__)
@@ -354,7 +399,8 @@ B2_HD void st_c(vec2<T>* p, const cpx<T>& c) {
 // INV (interleaved layout only) runs the same program with conjugated roots, i.e. the unscaled
 // inverse DFT.  Split-layout inverses are done by the host swapping the re/im plane pointers
 // (IDFT(z) = swap(DFT(swap z))), so SPLIT kernels are always compiled with INV = false.
-template <class Cfg, bool SPLIT, bool INV, bool FS = false>
+// POL: interleaved global loads / plain stores carry the L2 cache policies pol_in / pol_out (fused two-step kernel).
+template <class Cfg, bool SPLIT, bool INV, bool FS = false, bool POL = false>
 struct TileThread {
     using T = typename Cfg::T;
     using T2 = vec2<T>;
@@ -368,6 +414,7 @@ struct TileThread {
     long long base;       // element offset of (n = 0, this column) in the input
     long long obase;      // ... and in the output
     long long fs_n2i;     // FS: this column's n2
+    unsigned long long pol_in = 0, pol_out = 0;   // POL: L2 cache policies of the global loads / stores
 
     B2_HD void setup(int tid, long long bid, const PassParams<T>& p) {
         w = tid % W;
@@ -415,10 +462,23 @@ struct TileThread {
                 v[j] = cmake<T>(xr, xi);
             });
         } else {
+            if constexpr (W == 1 && !FS && !POL) {
+                if (p.in_blk_log2 >= 0 && p.in_blk[0] != nullptr) {      // source-blocked (pull) loads, see PassParams::in_blk
+                    const int lg = p.in_blk_log2;
+                    const int mask = (1 << lg) - 1;
+                    static_for<0, E>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const int n = t + TPC * j;
+                        v[j] = ld_stream_c(reinterpret_cast<const T2*>(p.in_blk[n >> lg]) + base + (n & mask));
+                    });
+                    return;
+                }
+            }
             const T2* pc = reinterpret_cast<const T2*>(p.in0) + base + (long long)t * p.inner;
             static_for<0, E>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                v[j] = ld_stream_c(pc + j * step);
+                if constexpr (POL) v[j] = ld_stream_c_pol(pc + j * step, pol_in);
+                else v[j] = ld_stream_c(pc + j * step);
             });
         }
     }
@@ -615,11 +675,47 @@ struct TileThread {
                 static_for<0, R>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
                     constexpr int q = i * R + brev(k, LG);
-                    st_c(pc + (i + k * BPT) * step, v[q]);
+                    if constexpr (POL) st_c_pol(pc + (i + k * BPT) * step, v[q], pol_out);
+                    else st_c(pc + (i + k * BPT) * step, v[q]);
                 });
             });
         }
     }
 };
+
+// ------------------------------------------------------------------ fused two-step strided program
+// An axis of length N = N1*N2 whose elements are `inner` apart, W adjacent columns at a time (a "super-tile"
+// of N x W elements, W*sizeof(complex) = 128 bytes per row), done by ONE CTA in one launch:
+//   step A  for every n2: length-N1 FFT over n1 (rows n1*N2 + n2), times w_N^(k1*n2), stored to the CTA's scratch
+//           slot as [n2][k1][W]              (sub-tiles of CfgA::G values of n2)
+//   step B  for every k1: length-N2 FFT over n2 read back from the scratch slot, output row k1 + N1*k2
+//           written to its final place       (sub-tiles of CfgB::G values of k1)
+// i.e. the four-step decomposition of api.cu add_axis(), but with both steps inside one kernel so that every
+// DRAM access is a full 128-byte line and the intermediate never leaves the L2 cache.  These two functions
+// place a thread of step A / step B; load(), the stages and store() are the ordinary tile thread program.
+template <class CfgA, class CfgB, class TH>
+B2_HD void fused2_setup_a(TH& th, int tid, int c, long long in_base, long long inner_in, long long slot) {
+    constexpr int W = CfgA::W;
+    th.w = tid % W;
+    th.t = (tid / W) % CfgA::TPC;
+    th.g = tid / (W * CfgA::TPC);
+    th.active = true;
+    const long long n2 = (long long)c * CfgA::G + th.g;
+    th.fs_n2i = n2;
+    th.base = in_base + n2 * inner_in + th.w;              // element n1 at + n1 * (N2*inner_in)
+    th.obase = slot + n2 * CfgA::N * W + th.w;             // scratch [n2][k1][W], k1 stride W
+}
+template <class CfgA, class CfgB, class TH>
+B2_HD void fused2_setup_b(TH& th, int tid, int c, long long out_base, long long inner_out, long long slot) {
+    constexpr int W = CfgB::W;
+    th.w = tid % W;
+    th.t = (tid / W) % CfgB::TPC;
+    th.g = tid / (W * CfgB::TPC);
+    th.active = true;
+    const long long k1 = (long long)c * CfgB::G + th.g;
+    th.fs_n2i = 0;
+    th.base = slot + k1 * W + th.w;                        // element n2 at + n2 * (N1*W)
+    th.obase = out_base + k1 * inner_out + th.w;           // output k = k1 + N1*k2 at + k2 * (N1*inner_out)
+}
 
 }  // namespace b2

@@ -509,6 +509,93 @@ tile_fft_kernel_tma_col_alias(const __grid_constant__ PassParams<typename Cfg::T
     if constexpr (BLK) __threadfence_system();
 }
 
+
+// ------------------------------------------------------------------ fused two-step strided kernel
+// Strided axes of length N >= 1024: a tile must be W = 128 bytes / sizeof(complex) columns wide for the memory
+// system to run near its peak (measured, profiles/r02_strided_copy_bw.txt: at >= 8 MiB row pitch HBM serves ~45 G
+// row pieces per second whatever their size up to 128 bytes, so 64-byte pieces cap a pass at 0.44 of the copy
+// bandwidth and 128-byte pieces reach 0.87; at 2-16 KiB pitch it is 0.70 against 1.0), but N x 128 bytes does not
+// fit the shared memory of one SM.  This kernel does the axis as N = N1*N2 in two steps inside ONE launch (see
+// fused2_setup_a/b in fft_core.cuh): each persistent CTA owns one super-tile at a time, every global access of both
+// steps is a full 128-byte line, and the [n2][k1][W] intermediate goes through a per-CTA scratch slot that is
+// rewritten every iteration and therefore lives in the 126 MB L2 -- one DRAM read and one DRAM write per element,
+// like the single-pass kernels.  While step B runs out of L2 the next super-tile is prefetched into L2.
+template <class CfgA, class CfgB, bool INV, int MINB>
+__global__ void __launch_bounds__(CfgA::THREADS, MINB)
+fused2_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, const __grid_constant__ PassParams<typename CfgA::T> pb,
+                  const long long inner_in, const long long inner_out) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    static_assert(CfgA::THREADS == CfgB::THREADS && CfgA::W == CfgB::W, "both steps run on the same CTA shape");
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N;
+    static_assert(N2 % CfgA::G == 0 && N1 % CfgB::G == 0, "sub-tiles must divide the super-tile");
+    constexpr int NSA = N2 / CfgA::G, NSB = N1 / CfgB::G;
+    extern __shared__ __align__(16) unsigned char b2_smem_raw[];
+    T2* smem = reinterpret_cast<T2*>(b2_smem_raw);
+    const int tid = (int)threadIdx.x;
+    const long long slot = (long long)blockIdx.x * ((long long)N1 * N2 * W);
+    // L2 policies: the input and output streams are touched once (evict first), the scratch slot is rewritten every
+    // iteration and must stay resident (evict last); step B drops every scratch line it has consumed (discard.L2) so that
+    // the dirty intermediate is never written back to DRAM
+    unsigned long long pol_stream, pol_scratch;
+    {
+        unsigned long long pf, pl, pn;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+        pol_stream = (pa.fused_flags & 4) ? pf : pn;
+        pol_scratch = (pa.fused_flags & 8) ? pl : pn;
+    }
+    for (long long s = blockIdx.x; s < pa.n_tiles; s += gridDim.x) {
+        const long long o = s / pa.inner_blocks, ib = s - o * pa.inner_blocks;
+        {
+            TileThread<CfgA, false, INV, true, true> th;
+            th.pol_in = pol_stream; th.pol_out = pol_scratch;
+            const long long in_base = o * pa.outer_stride + ib * W;
+#pragma unroll 1
+            for (int c = 0; c < NSA; ++c) {
+                fused2_setup_a<CfgA, CfgB>(th, tid, c, in_base, inner_in, slot);
+                th.load(pa);
+                run_stages<CfgA, false, INV, 0>(th, pa, smem);
+                th.store(pa);
+                if constexpr (CfgA::S > 1) __syncthreads();      // exchange buffer fully read before the next sub-tile
+            }
+        }
+        __syncthreads();                                         // the whole intermediate is in the scratch slot
+        {
+            const long long s2 = s + gridDim.x;                  // next super-tile of this CTA -> L2
+            if ((pa.fused_flags & 2) && s2 < pa.n_tiles) {
+                const long long o2 = s2 / pa.inner_blocks, ib2 = s2 - o2 * pa.inner_blocks;
+                const T2* nb = reinterpret_cast<const T2*>(pa.in0) + o2 * pa.outer_stride + ib2 * W;
+                for (int r = tid; r < N1 * N2; r += CfgA::THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (long long)r * inner_in));
+            }
+        }
+        {
+            TileThread<CfgB, false, INV, false, true> th;
+            th.pol_in = pol_scratch; th.pol_out = pol_stream;
+            const long long out_base = o * pb.out_outer_stride + ib * W;
+#pragma unroll 1
+            for (int c = 0; c < NSB; ++c) {
+                fused2_setup_b<CfgA, CfgB>(th, tid, c, out_base, inner_out, slot);
+                th.load(pb);
+                run_stages<CfgB, false, INV, 0>(th, pb, smem);
+                th.store(pb);
+                if (pa.fused_flags & 1) {
+                    // the W lanes that share a scratch row have consumed it (their loads fed the butterflies above): drop the
+                    // 128-byte lines of this thread row, lane w taking rows j = w, w + W, ..
+                    __syncwarp();
+                    const T2* row0 = reinterpret_cast<const T2*>(pb.in0) + (th.base - th.w) + (long long)th.t * pb.inner;
+                    for (int j = th.w; j < CfgB::E; j += W)
+                        asm volatile("discard.global.L2 [%0], 128;" ::"l"(row0 + (long long)j * CfgB::TPC * pb.inner) : "memory");
+                }
+                if constexpr (CfgB::S > 1) __syncthreads();
+            }
+        }
+        __syncthreads();                                         // slot fully read before the next super-tile overwrites it
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -519,7 +606,8 @@ struct KernelVariant {
     int threads;
     long long smem_bytes;
     int minb;
-    int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis), 2 = persistent + TMA tensor staging (strided axes)
+    int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis), 2 = persistent + TMA tensor staging (strided axes),
+                     // 3 = fused two-step strided kernel (N = N1*N2 through an L2-resident scratch slot per CTA)
     int nbuf;        // ring depth for kind 1
     int blk;         // 1: also compiled with destination-blocked stores (slab exchange passes)
     int fs;          // 1: also compiled as a four-step "A" pass (transposed store + inter-pass twiddle)
@@ -528,6 +616,13 @@ struct KernelVariant {
     cudaError_t (*prepare)();   // one-time function attributes (dynamic smem opt-in)
     // occupancy (CTAs/SM) of the interleaved forward kernel, for the tuning report
     int (*occupancy)();
+    // kind 3 only: step A is log2n1 long with radices radix[]/S/E, step B has radix_b[]/S_b/E_b; the scratch buffer
+    // needs slot_elems complex elements for each of the grid_slots() CTAs the launch may use
+    int log2n1;
+    int S_b, E_b;
+    int radix_b[4];
+    long long slot_elems;
+    int (*grid_slots)();
 };
 
 template <class Cfg, int MINB, bool BLKCAP = false, bool FSCAP = false>
@@ -877,6 +972,88 @@ struct VariantOpsTmaColAlias {
     }
 };
 
+
+template <class CfgA, class CfgB, int MINB>
+struct VariantOpsFused2 {
+    using T = typename CfgA::T;
+    static constexpr size_t SMEM = (size_t)(CfgA::SMEM_BYTES > CfgB::SMEM_BYTES ? CfgA::SMEM_BYTES : CfgB::SMEM_BYTES);
+    static int& slots() { static int s = 0; return s; }
+    static cudaError_t prepare() {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(fused2_fft_kernel<CfgA, CfgB, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(fused2_fft_kernel<CfgA, CfgB, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM)) != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused2_fft_kernel<CfgA, CfgB, false, MINB>, CfgA::THREADS, SMEM);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return cudaSuccess;
+    }
+    static int grid_slots() {
+        if (slots() <= 0 && prepare() != cudaSuccess) return -1;
+        return slots();
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        if (split || p.out_blk_log2 >= 0 || p.outer_div > 0 || !p.scratch || !p.fs_t2) return cudaErrorNotSupported;
+        if (p.n_tiles <= 0) return cudaSuccess;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        long long ctas = p.n_tiles;
+        if (ctas > slots()) ctas = slots();
+        if (ctas > p.scratch_slots) ctas = p.scratch_slots;
+        if (p.max_ctas > 0 && ctas > p.max_ctas) ctas = p.max_ctas;
+        if (ctas <= 0) return cudaErrorInvalidValue;
+        PassParams<T> pa = p, pb = p;
+        pa.inner = (long long)CfgB::N * p.inner;          // n1 stride
+        pa.out0 = p.scratch;
+        pa.out_inner = CfgA::W;
+        pa.scale_mode = 0;
+        pa.fs_n2 = CfgB::N;
+        pb.in0 = p.scratch;
+        pb.inner = (long long)CfgA::N * CfgA::W;          // n2 stride inside the scratch slot
+        pb.out_inner = (long long)CfgA::N * p.out_inner;  // k2 stride in the output
+        for (int s = 0; s < 3; ++s) pb.tw[s] = p.tw_b[s];
+        pb.fs_t1 = pb.fs_t2 = nullptr;
+        static const int flags = [] { const char* e = getenv("B2FFT_FUSED_FLAGS"); return e ? atoi(e) : 13; }();
+        // discard needs 128-byte aligned scratch rows (W * sizeof(complex) == 128 and a 128-byte aligned buffer)
+        pa.fused_flags = pb.fused_flags = (((uintptr_t)p.scratch % 128) == 0 && CfgA::W * 2 * sizeof(T) == 128) ? flags : (flags & ~1);
+        const dim3 grid((unsigned)ctas), block(CfgA::THREADS);
+        if (inv) fused2_fft_kernel<CfgA, CfgB, true, MINB><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        else fused2_fft_kernel<CfgA, CfgB, false, MINB><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused2_fft_kernel<CfgA, CfgB, false, MINB>, CfgA::THREADS, SMEM) !=
+            cudaSuccess)
+            return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v{};
+        v.name = name;
+        v.prec = sizeof(T) == 4 ? 0 : 1;
+        v.log2n = CfgA::LOG2N + CfgB::LOG2N;
+        v.log2n1 = CfgA::LOG2N;
+        v.W = CfgA::W; v.G = CfgA::G; v.E = CfgA::E; v.S = CfgA::S;
+        v.S_b = CfgB::S; v.E_b = CfgB::E;
+        for (int s = 0; s < 4; ++s) { v.radix[s] = s < CfgA::S ? CfgA::R(s) : 1; v.radix_b[s] = s < CfgB::S ? CfgB::R(s) : 1; }
+        v.threads = CfgA::THREADS;
+        v.smem_bytes = (long long)SMEM;
+        v.minb = MINB;
+        v.kind = 3;
+        v.slot_elems = (long long)CfgA::N * CfgB::N * CfgA::W;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        v.grid_slots = &grid_slots;
+        return v;
+    }
+};
+
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x
 #define B2_STR(x) B2_STR2(x)
@@ -925,11 +1102,19 @@ struct VariantOpsTmaColAlias {
     out.push_back(::b2::VariantOpsTmaColAlias<::b2::TileCfg<T, L, W, G, R0, R1, R2, R3>, MB>::make(    \
         #T "_n" B2_STR(L) "_w" B2_STR(W) "_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmaca"));
 
+// B2_VU(type, log2n1, log2n2, W, GA, GB, minblocks, A radices R0..R3, B radices R0..R3): fused two-step strided variant
+#define B2_VU(T, L1, L2, W, GA, GB, MB, A0, A1, A2, A3, B0, B1, B2_, B3)                              \
+    out.push_back(::b2::VariantOpsFused2<::b2::TileCfg<T, L1, W, GA, A0, A1, A2, A3>,                  \
+                                         ::b2::TileCfg<T, L2, W, GB, B0, B1, B2_, B3>, MB>::make(      \
+        #T "_n" B2_STR(L1) "+" B2_STR(L2) "_w" B2_STR(W) "_g" B2_STR(GA) "+" B2_STR(GB) "_b" B2_STR(MB) "_r" B2_STR(A0) "x" B2_STR(A1) "x" B2_STR(A2) "+" B2_STR(B0) "x" B2_STR(B1) "x" B2_STR(B2_) "_fused2"));
+
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);
 void register_f64_row(std::vector<KernelVariant>& out);
 void register_f64_col(std::vector<KernelVariant>& out);
 void register_exp(std::vector<KernelVariant>& out);
 void register_exp2(std::vector<KernelVariant>& out);
+void register_fused(std::vector<KernelVariant>& out);
+void register_fused_exp(std::vector<KernelVariant>& out);
 
 }  // namespace b2

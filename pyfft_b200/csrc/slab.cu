@@ -1,0 +1,400 @@
+// Slab-decomposed 3-D C2C transform over several GPUs: one rank's schedule, behind the C ABI
+// (include/b2fft.h, b2fft_slab_*).  No reference counterpart: the reference is single-device
+// (pyfft/plan.py:204-245 runs every kernel of a plan on one stream of one context).
+//
+// Layout.  Rank g holds z in [g*Zl, (g+1)*Zl) of a (Z, Y, X) array as the z-slab [Zl][Y][X].  After the
+// forward transform rank h holds x in [h*Xb, (h+1)*Xb) as the x-slab [Y][Z][Xb] ("transposed out": one
+// exchange, the result stays distributed).
+//
+// Forward schedule (all on the device, no host synchronisation, no NCCL on the data path):
+//   main stream   : "my x-slab may be overwritten" -> ready flag of this rank on every peer
+//                   for each z-chunk k:  Y pass of chunk k (local, in place)
+//   exchange strm : for each z-chunk k (after its Y pass), for each y-chunk c:
+//                       X pass of rows {z in chunk k} x {y in chunk c}; its stores are destination-blocked:
+//                       x-block h of every output row goes, as one contiguous X/G-element piece, straight into
+//                       rank h's x-slab over NVLink (cp.async.bulk from shared memory or 256-byte warp stores)
+//                   after the last z-chunk of y-chunk c: flag (rank, c) on every peer (st.release.sys)
+//   Z stream      : for each y-chunk c: spin on the flags (all ranks, c) in local memory (ld.acquire.sys), then
+//                   the Z pass of that chunk's rows (row pitch Xb) -- it runs beside the NVLink stores of the
+//                   following chunks.
+// The cross-rank synchronisation is a word per (rank, chunk) in peer-mapped device memory carrying a
+// monotonically increasing epoch; nothing waits on the host and no collective library is involved.
+//
+// Inverse schedule (x-slabs -> z-slabs): inverse Z pass per y-chunk in place, flag per chunk, then the X pass
+// of every (z, y) row PULLS its G pieces from the peers' x-slabs with TMA bulk loads (source-blocked loads,
+// the mirror image of the forward stores), then the local inverse Y pass applies the scale.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2fft.h"
+
+namespace {
+
+int slab_fail(int code, const char* fmt, ...);
+
+__global__ void slab_signal_kernel(unsigned* const* peer_flags, int n_peers, int word, unsigned value) {
+    const int h = (int)threadIdx.x;
+    if (h < n_peers) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[h] + word), "r"(value) : "memory");
+    }
+}
+
+// thread i waits until flags[first + i*stride] has reached `value` (epochs only grow; wrap-safe compare)
+__global__ void slab_wait_kernel(const unsigned* flags, int first, int stride, int n, unsigned value, unsigned* err,
+                                 long long timeout_cycles) {
+    const int i = (int)threadIdx.x;
+    if (i < n) {
+        const unsigned* p = flags + first + (long long)i * stride;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            if ((int)(v - value) >= 0) break;
+            if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1u + (unsigned)i); break; }   // never hang the GPU
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+thread_local std::string g_slab_err;
+
+int slab_fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_slab_err = buf;
+    return code;
+}
+
+#define SLAB_CUDA(expr)                                                                                      \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return slab_fail(B2FFT_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));    \
+    } while (0)
+#define SLAB_TRY(expr)                                                \
+    do {                                                              \
+        int rc__ = (expr);                                            \
+        if (rc__ != B2FFT_OK) return slab_fail(rc__, "%s: %s", #expr, b2fft_last_error()); \
+    } while (0)
+
+struct DevGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DevGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct b2fft_slab_plan {
+    long long X, Y, Z, Zl, Xb, Yc, Zk;
+    int G, rank, device, prec, C, K;
+    size_t esz;
+    b2fft_plan *fwd_y = nullptr, *fwd_x = nullptr, *fwd_z = nullptr;      // forward sub-plans
+    b2fft_plan *inv_z = nullptr, *inv_x = nullptr, *inv_y = nullptr;      // inverse sub-plans
+    void* ws[6] = {};                                                     // plan-owned workspaces of sub-plans that need one
+    char* slab = nullptr;
+    std::vector<char*> xslab;             // xslab of every rank, as addressable from this device
+    std::vector<unsigned*> flags;         // flag words of every rank
+    unsigned** d_flag_ptrs = nullptr;     // device copy of `flags`
+    unsigned* d_err = nullptr;
+    cudaStream_t sx = nullptr, sz = nullptr;
+    std::vector<cudaEvent_t> ev_y;        // Y pass of z-chunk k done
+    cudaEvent_t ev_start = nullptr, ev_sx = nullptr, ev_sz = nullptr;
+    unsigned epoch = 0;                   // one per forward / inverse call
+    unsigned last_inverse_epoch = 0;      // peers pulled from my x-slab during that call
+    bool attached = false;
+    long long timeout_cycles = 20LL * 1000 * 1000 * 1000;   // ~10 s at 2 GHz
+    // flag word layout (each word written by exactly one remote rank)
+    int w_ready(int src) const { return src; }
+    int w_chunk(int src, int c) const { return G + src * C + c; }
+    int w_inv_chunk(int src, int c) const { return G + G * C + src * C + c; }
+    int w_inv_done(int src) const { return G + 2 * G * C + src; }
+    int n_words() const { return 2 * G + 2 * G * C; }
+};
+
+extern "C" {
+
+const char* b2fft_slab_last_error(void) { return g_slab_err.c_str(); }
+
+int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int precision, int normalize, double scale,
+                           int fast_math, int device, int rank, int nranks, int y_chunks, int z_chunks,
+                           int exchange_ctas_per_sm) {
+    if (!out || !dims_xyz) return slab_fail(B2FFT_E_INVALID, "null argument");
+    *out = nullptr;
+    const long long X = dims_xyz[0], Y = dims_xyz[1], Z = dims_xyz[2];
+    const int G = nranks;
+    if (G < 1 || G > 16 || (G & (G - 1))) return slab_fail(B2FFT_E_INVALID, "number of ranks must be a power of two <= 16");
+    if (rank < 0 || rank >= G) return slab_fail(B2FFT_E_INVALID, "bad rank %d of %d", rank, G);
+    if (X < 1 || Y < 1 || Z < 1 || (X & (X - 1)) || (Y & (Y - 1)) || (Z & (Z - 1)))
+        return slab_fail(B2FFT_E_INVALID, "Array dimensions must be powers of two");
+    if (Z % G || X % G) return slab_fail(B2FFT_E_INVALID, "Z and X must be divisible by the number of ranks");
+    if (precision != B2FFT_F32 && precision != B2FFT_F64) return slab_fail(B2FFT_E_INVALID, "bad precision %d", precision);
+    DevGuard guard(device);
+    b2fft_slab_plan* sp = new b2fft_slab_plan();
+    sp->X = X; sp->Y = Y; sp->Z = Z; sp->G = G; sp->rank = rank; sp->device = device; sp->prec = precision;
+    sp->Zl = Z / G; sp->Xb = X / G;
+    sp->esz = precision ? 16 : 8;
+    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : 1;
+    if (C > Y) C = Y;
+    while (Y % C) --C;
+    if (K > sp->Zl) K = sp->Zl;
+    while (sp->Zl % K) --K;
+    sp->C = (int)C; sp->K = (int)K;
+    sp->Yc = Y / C; sp->Zk = sp->Zl / K;
+    const double nsize = (double)X * (double)Y * (double)Z;
+    auto fail_free = [&](int rc) { b2fft_slab_plan_destroy(sp); return rc; };
+    auto mk = [&](b2fft_plan** p, long long x, long long y, long long z, int axes, int apply_scale) {
+        const int64_t d[3] = {x, y, z};
+        return b2fft_plan_create_ex(p, d, axes, precision, B2FFT_INTERLEAVED, normalize, scale, fast_math, device, nsize, apply_scale);
+    };
+    int rc;
+    // forward: Y pass per z-chunk, X pass per (z-chunk, y-chunk) with blocked stores, Z pass per y-chunk with the scale
+    if ((rc = mk(&sp->fwd_y, X, Y, sp->Zk, B2FFT_AXIS_Y, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    if ((rc = mk(&sp->fwd_x, X, sp->Yc, sp->Zk, B2FFT_AXIS_X, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    if ((rc = mk(&sp->fwd_z, sp->Xb, Z, sp->Yc, B2FFT_AXIS_Y, 1)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    // inverse: Z pass per y-chunk, X pass per y-chunk pulling from the peers, Y pass over the whole slab with the scale
+    if ((rc = mk(&sp->inv_z, sp->Xb, Z, sp->Yc, B2FFT_AXIS_Y, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    if ((rc = mk(&sp->inv_x, X, sp->Yc, sp->Zl, B2FFT_AXIS_X, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    if ((rc = mk(&sp->inv_y, X, Y, sp->Zl, B2FFT_AXIS_Y, 1)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    if (G > 1 && exchange_ctas_per_sm > 0 &&
+        (rc = b2fft_plan_set_exchange_ctas(sp->fwd_x, exchange_ctas_per_sm)) != B2FFT_OK)
+        return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    // sub-plans whose local axis is too long for one pass need scratch memory: owned here (in-place executes)
+    b2fft_plan* subs[6] = {sp->fwd_y, sp->fwd_x, sp->fwd_z, sp->inv_z, sp->inv_x, sp->inv_y};
+    for (int i = 0; i < 6; ++i) {
+        size_t need = 0;
+        if ((rc = b2fft_plan_workspace_bytes_ex(subs[i], 1, 1, &need)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+        if (i == 1 || i == 4) {
+            if (need) return fail_free(slab_fail(B2FFT_E_UNSUPPORTED, "X = %lld is too long for the single-pass exchange kernel", X));
+            continue;
+        }
+        if (need) {
+            cudaError_t e = cudaMalloc(&sp->ws[i], need);
+            if (e != cudaSuccess) return fail_free(slab_fail(B2FFT_E_CUDA, "cudaMalloc of a %zu byte workspace: %s", need, cudaGetErrorString(e)));
+            if ((rc = b2fft_plan_set_workspace(subs[i], sp->ws[i], need)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+        }
+    }
+    cudaError_t e;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithFlags(&sp->sx, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&sp->sz, cudaStreamNonBlocking, hi)) != cudaSuccess)
+        return fail_free(slab_fail(B2FFT_E_CUDA, "stream creation: %s", cudaGetErrorString(e)));
+    sp->ev_y.resize(sp->K);
+    for (auto& ev : sp->ev_y)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess)
+            return fail_free(slab_fail(B2FFT_E_CUDA, "event creation: %s", cudaGetErrorString(e)));
+    if ((e = cudaEventCreateWithFlags(&sp->ev_start, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&sp->ev_sx, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&sp->ev_sz, cudaEventDisableTiming)) != cudaSuccess)
+        return fail_free(slab_fail(B2FFT_E_CUDA, "event creation: %s", cudaGetErrorString(e)));
+    if ((e = cudaMalloc(&sp->d_err, sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(sp->d_err, 0, sizeof(unsigned))) != cudaSuccess)
+        return fail_free(slab_fail(B2FFT_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)));
+    *out = sp;
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_sizes(const b2fft_slab_plan* sp, size_t* slab_bytes, size_t* xslab_bytes, size_t* flag_bytes) {
+    if (!sp) return slab_fail(B2FFT_E_INVALID, "null plan");
+    if (slab_bytes) *slab_bytes = (size_t)(sp->Zl * sp->Y * sp->X) * sp->esz;
+    if (xslab_bytes) *xslab_bytes = (size_t)(sp->Y * sp->Z * sp->Xb) * sp->esz;
+    if (flag_bytes) *flag_bytes = (size_t)sp->n_words() * sizeof(unsigned);
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_geometry(const b2fft_slab_plan* sp, int64_t out[8]) {
+    if (!sp || !out) return slab_fail(B2FFT_E_INVALID, "null argument");
+    out[0] = sp->Zl; out[1] = sp->Xb; out[2] = sp->C; out[3] = sp->K; out[4] = sp->Yc; out[5] = sp->Zk; out[6] = sp->G; out[7] = sp->rank;
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_attach(b2fft_slab_plan* sp, void* slab, void* const* xslab_of_rank, void* const* flags_of_rank) {
+    if (!sp || !slab || !xslab_of_rank || !flags_of_rank) return slab_fail(B2FFT_E_INVALID, "null argument");
+    DevGuard guard(sp->device);
+    sp->slab = (char*)slab;
+    sp->xslab.assign(sp->G, nullptr);
+    sp->flags.assign(sp->G, nullptr);
+    for (int r = 0; r < sp->G; ++r) {
+        if (!xslab_of_rank[r] || !flags_of_rank[r]) return slab_fail(B2FFT_E_INVALID, "null buffer of rank %d", r);
+        if (((uintptr_t)xslab_of_rank[r] % 16) || ((uintptr_t)flags_of_rank[r] % 4)) return slab_fail(B2FFT_E_INVALID, "misaligned buffer of rank %d", r);
+        sp->xslab[r] = (char*)xslab_of_rank[r];
+        sp->flags[r] = (unsigned*)flags_of_rank[r];
+    }
+    if (((uintptr_t)slab % 16)) return slab_fail(B2FFT_E_INVALID, "misaligned slab");
+    if (!sp->d_flag_ptrs) SLAB_CUDA(cudaMalloc(&sp->d_flag_ptrs, 16 * sizeof(unsigned*)));
+    SLAB_CUDA(cudaMemcpy(sp->d_flag_ptrs, sp->flags.data(), sp->G * sizeof(unsigned*), cudaMemcpyHostToDevice));
+    // my own flag words start at epoch 0 (the owner clears them; peers only ever write epochs >= 1)
+    SLAB_CUDA(cudaMemset(sp->flags[sp->rank], 0, (size_t)sp->n_words() * sizeof(unsigned)));
+    SLAB_CUDA(cudaDeviceSynchronize());
+    sp->attached = true;
+    return B2FFT_OK;
+}
+
+static int slab_signal(b2fft_slab_plan* sp, int word, cudaStream_t st) {
+    slab_signal_kernel<<<1, 32, 0, st>>>(sp->d_flag_ptrs, sp->G, word, sp->epoch);
+    SLAB_CUDA(cudaGetLastError());
+    return B2FFT_OK;
+}
+static int slab_wait(b2fft_slab_plan* sp, int first, int stride, unsigned value, cudaStream_t st) {
+    slab_wait_kernel<<<1, 32, 0, st>>>(sp->flags[sp->rank], first, stride, sp->G, value, sp->d_err, sp->timeout_cycles);
+    SLAB_CUDA(cudaGetLastError());
+    return B2FFT_OK;
+}
+
+int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
+    if (!sp || !sp->attached) return slab_fail(B2FFT_E_INVALID, "slab plan has no buffers attached");
+    DevGuard guard(sp->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t esz = sp->esz;
+    const int G = sp->G, C = sp->C, K = sp->K;
+    ++sp->epoch;
+    if (G > 1) {
+        // peers may still be pulling from my x-slab (previous inverse): wait for them, then tell everybody that my
+        // x-slab may be overwritten (everything queued on `s` before this call has consumed it)
+        if (sp->last_inverse_epoch) SLAB_TRY(slab_wait(sp, sp->w_inv_done(0), 1, sp->last_inverse_epoch, s));
+        SLAB_TRY(slab_signal(sp, sp->w_ready(sp->rank), s));
+    }
+    SLAB_CUDA(cudaEventRecord(sp->ev_start, s));
+    SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_start, 0));
+    std::vector<void*> blk(G);
+    for (int k = 0; k < K; ++k) {
+        char* zk = sp->slab + (size_t)k * sp->Zk * sp->Y * sp->X * esz;
+        SLAB_TRY(b2fft_execute(sp->fwd_y, zk, nullptr, zk, nullptr, 0, 1, s));
+        SLAB_CUDA(cudaEventRecord(sp->ev_y[k], s));
+        SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[k], 0));
+        if (k == 0 && G > 1) SLAB_TRY(slab_wait(sp, sp->w_ready(0), 1, sp->epoch, sp->sx));
+        for (int c = 0; c < C; ++c) {
+            // rows {z in chunk k} x {y in chunk c}: row (z, y) starts at slab[(z*Y + y)*X]; its x-block h goes to
+            // xslab_h[(y*Z + rank*Zl + z)*Xb]
+            char* src = zk + (size_t)c * sp->Yc * sp->X * esz;
+            for (int h = 0; h < G; ++h)
+                blk[h] = sp->xslab[h] + ((size_t)c * sp->Yc * sp->Z + (size_t)sp->rank * sp->Zl + (size_t)k * sp->Zk) * sp->Xb * esz;
+            SLAB_TRY(b2fft_plan_set_output_blocks(sp->fwd_x, G, blk.data(), nullptr, 1, sp->Z * sp->Xb));
+            SLAB_TRY(b2fft_plan_set_outer_split(sp->fwd_x, sp->Yc, sp->X, sp->Y * sp->X, sp->Z * sp->Xb, sp->Xb));
+            SLAB_TRY(b2fft_execute(sp->fwd_x, src, nullptr, src, nullptr, 0, 1, sp->sx));
+            if (k == K - 1) {
+                if (G > 1) {
+                    SLAB_TRY(slab_signal(sp, sp->w_chunk(sp->rank, c), sp->sx));
+                    SLAB_TRY(slab_wait(sp, sp->w_chunk(0, c), C, sp->epoch, sp->sz));
+                } else {
+                    SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
+                    SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_sx, 0));
+                }
+                char* zc = sp->xslab[sp->rank] + (size_t)c * sp->Yc * sp->Z * sp->Xb * esz;
+                SLAB_TRY(b2fft_execute(sp->fwd_z, zc, nullptr, zc, nullptr, 0, 1, sp->sz));
+            }
+        }
+    }
+    SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
+    SLAB_CUDA(cudaEventRecord(sp->ev_sz, sp->sz));
+    SLAB_CUDA(cudaStreamWaitEvent(s, sp->ev_sx, 0));
+    SLAB_CUDA(cudaStreamWaitEvent(s, sp->ev_sz, 0));
+    return B2FFT_OK;
+}
+
+int b2fft_slab_inverse(b2fft_slab_plan* sp, void* cuda_stream) {
+    if (!sp || !sp->attached) return slab_fail(B2FFT_E_INVALID, "slab plan has no buffers attached");
+    DevGuard guard(sp->device);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const size_t esz = sp->esz;
+    const int G = sp->G, C = sp->C;
+    ++sp->epoch;
+    // the in-place Z pass below overwrites my x-slab: peers must have finished pulling from it (previous inverse)
+    if (G > 1 && sp->last_inverse_epoch) SLAB_TRY(slab_wait(sp, sp->w_inv_done(0), 1, sp->last_inverse_epoch, s));
+    SLAB_CUDA(cudaEventRecord(sp->ev_start, s));
+    SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_start, 0));
+    std::vector<const void*> src(G);
+    for (int c = 0; c < C; ++c) {
+        char* zc = sp->xslab[sp->rank] + (size_t)c * sp->Yc * sp->Z * sp->Xb * esz;
+        SLAB_TRY(b2fft_execute(sp->inv_z, zc, nullptr, zc, nullptr, 1, 1, s));
+        if (G > 1) {
+            SLAB_TRY(slab_signal(sp, sp->w_inv_chunk(sp->rank, c), s));
+            SLAB_TRY(slab_wait(sp, sp->w_inv_chunk(0, c), C, sp->epoch, sp->sx));
+        } else {
+            SLAB_CUDA(cudaEventRecord(sp->ev_y[0], s));
+            SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[0], 0));
+        }
+        // rows {all local z} x {y in chunk c}: piece h of row (z, y) is xslab_h[(y*Z + rank*Zl + z)*Xb .. +Xb)
+        for (int h = 0; h < G; ++h)
+            src[h] = sp->xslab[h] + ((size_t)c * sp->Yc * sp->Z + (size_t)sp->rank * sp->Zl) * sp->Xb * esz;
+        char* dst = sp->slab + (size_t)c * sp->Yc * sp->X * esz;
+        SLAB_TRY(b2fft_plan_set_input_blocks(sp->inv_x, G, src.data()));
+        SLAB_TRY(b2fft_plan_set_outer_split(sp->inv_x, sp->Yc, sp->Z * sp->Xb, sp->Xb, sp->X, sp->Y * sp->X));
+        SLAB_TRY(b2fft_execute(sp->inv_x, dst, nullptr, dst, nullptr, 1, 1, sp->sx));
+    }
+    if (G > 1) SLAB_TRY(slab_signal(sp, sp->w_inv_done(sp->rank), sp->sx));
+    sp->last_inverse_epoch = sp->epoch;
+    SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
+    SLAB_CUDA(cudaStreamWaitEvent(s, sp->ev_sx, 0));
+    SLAB_TRY(b2fft_execute(sp->inv_y, sp->slab, nullptr, sp->slab, nullptr, 1, 1, s));
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_status(b2fft_slab_plan* sp, int* out) {
+    if (!sp || !out) return slab_fail(B2FFT_E_INVALID, "null argument");
+    DevGuard guard(sp->device);
+    unsigned v = 0;
+    SLAB_CUDA(cudaMemcpy(&v, sp->d_err, sizeof v, cudaMemcpyDeviceToHost));
+    *out = (int)v;
+    return B2FFT_OK;
+}
+
+int64_t b2fft_slab_plan_launch_count(const b2fft_slab_plan* sp) {
+    if (!sp) return -1;
+    int64_t n = 0;
+    const b2fft_plan* subs[6] = {sp->fwd_y, sp->fwd_x, sp->fwd_z, sp->inv_z, sp->inv_x, sp->inv_y};
+    for (auto* p : subs)
+        if (p) n += b2fft_plan_launch_count(p);
+    return n;
+}
+
+int b2fft_slab_plan_describe(const b2fft_slab_plan* sp, char* buf, size_t buflen) {
+    if (!sp || !buf || !buflen) return slab_fail(B2FFT_E_INVALID, "bad argument");
+    char line[1024], a[256], b[256], c[256];
+    b2fft_plan_describe(sp->fwd_y, a, sizeof a);
+    b2fft_plan_describe(sp->fwd_x, b, sizeof b);
+    b2fft_plan_describe(sp->fwd_z, c, sizeof c);
+    for (char* s : {a, b, c})
+        if (char* nl = strchr(s, '\n')) *nl = 0;
+    snprintf(line, sizeof line,
+             "rank %d/%d: z-slab [%lld][%lld][%lld] -> x-slab [%lld][%lld][%lld]; %d z-chunk(s) x %d y-chunk(s); "
+             "Y pass {%s} | X pass + NVLink-blocked stores {%s} | peer flags | Z pass {%s}",
+             sp->rank, sp->G, sp->Zl, sp->Y, sp->X, sp->Y, sp->Z, sp->Xb, sp->K, sp->C, a, b, c);
+    snprintf(buf, buflen, "%s", line);
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_destroy(b2fft_slab_plan* sp) {
+    if (!sp) return B2FFT_OK;
+    DevGuard guard(sp->device);
+    b2fft_plan* subs[6] = {sp->fwd_y, sp->fwd_x, sp->fwd_z, sp->inv_z, sp->inv_x, sp->inv_y};
+    for (auto* p : subs)
+        if (p) b2fft_plan_destroy(p);
+    for (void* w : sp->ws)
+        if (w) cudaFree(w);
+    if (sp->sx) cudaStreamDestroy(sp->sx);
+    if (sp->sz) cudaStreamDestroy(sp->sz);
+    for (auto ev : sp->ev_y)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {sp->ev_start, sp->ev_sx, sp->ev_sz})
+        if (ev) cudaEventDestroy(ev);
+    if (sp->d_flag_ptrs) cudaFree(sp->d_flag_ptrs);
+    if (sp->d_err) cudaFree(sp->d_err);
+    delete sp;
+    return B2FFT_OK;
+}
+
+}  // extern "C"

@@ -14,6 +14,7 @@ void register_f32_col(std::vector<KernelVariant>& out) {
 #define X0 B2_V0
 #define XT0 B2_VT0
 #define XC0 B2_VC0
+#define XU B2_VU
 #include "variants.def"
 #undef X
 #undef XT
@@ -25,5 +26,6 @@ void register_f32_col(std::vector<KernelVariant>& out) {
 #undef X0
 #undef XT0
 #undef XC0
+#undef XU
 }
 }  // namespace b2

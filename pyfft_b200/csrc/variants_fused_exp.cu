@@ -1,9 +1,9 @@
-// Kernel instantiations for group EXP (see variants.def).
+// Kernel instantiations for group FUSED_EXP (see variants.def).
 #include "kernels.cuh"
 
 namespace b2 {
-void register_exp(std::vector<KernelVariant>& out) {
-#define B2_GROUP_EXP
+void register_fused_exp(std::vector<KernelVariant>& out) {
+#define B2_GROUP_FUSED_EXP
 #define X B2_V
 #define XT B2_VT
 #define XC B2_VC

@@ -149,7 +149,7 @@ class SlabPlan(object):
     """
 
     def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
-                 exchange="p2p", device=None, yslab_layout="zyx", chunks=1, exchange_ctas_per_sm=2):
+                 exchange="xslab", device=None, yslab_layout="zyx", chunks=1, exchange_ctas_per_sm=3, z_chunks=1):
         import torch
         import torch.distributed as dist
         if len(shape) != 3:
@@ -165,6 +165,9 @@ class SlabPlan(object):
         # chunk c runs on a side stream while the X/Y passes of chunk c+1 compute
         self.chunks = max(1, int(chunks))
         self.exchange_ctas_per_sm = int(exchange_ctas_per_sm)
+        self.z_chunks = max(1, int(z_chunks))
+        self._normalize, self._scale, self._fast_math = bool(normalize), float(scale), bool(fast_math)
+        self._native = None
         self._torch, self._dist = torch, dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -246,96 +249,88 @@ class SlabPlan(object):
             self._set_blocks(self._fwd_xy, [self._yslab_buf.ptr], L["fwd_out_inner" + sfx], L["fwd_out_outer_stride" + sfx])
             self._set_blocks(self._inv_z, [self._slab_buf.ptr], L["inv_out_inner"], L["inv_out_outer_stride" + sfx])
 
-    # ------------------------------------------------------------------ x-slab mode
+    # ------------------------------------------------------------------ x-slab mode (native: csrc/slab.cu)
     def _init_xslab(self):
-        """Forward: Y pass (local, in place) -> X pass in y-chunks whose destination-blocked stores put
-        x-block h of every row straight into rank h's x-slab ``[Y][Z][Xb]`` over NVLink (2 KiB
-        contiguous pieces at 2048^3 on 8 GPUs, against the 32-64 byte pieces a strided pass can
-        offer) -> per chunk: cross-rank barrier, Z pass on that chunk's rows (pitch Xb, TMA-staged)
-        while the next chunk's stores are in flight."""
+        """The whole schedule lives behind the C ABI (``b2fft_slab_*``, csrc/slab.cu): local Y pass per z-chunk, X pass
+        per (z-chunk, y-chunk) whose destination-blocked stores put x-block h of every row straight into rank h's
+        x-slab ``[Y][Z][Xb]`` over NVLink, one epoch word per (rank, y-chunk) in peer-mapped memory as the cross-rank
+        signal, Z pass per y-chunk beside the stores of the following chunks; the inverse pulls the pieces back inside
+        its X pass.  This class allocates the peer-visible buffers, exchanges their CUDA IPC handles through
+        torch.distributed and attaches them."""
         torch, dist, L, lib = self._torch, self._dist, self.L, self._lib
         X, Y, Z, Zl, G = L["X"], L["Y"], L["Z"], L["Zl"], self.world
         if X % G:
             raise ValueError("X must be divisible by the number of ranks for the x-slab exchange")
+        h = ctypes.c_void_p()
+        dims = (ctypes.c_int64 * 3)(X, Y, Z)
+        self._check(lib.b2fft_slab_plan_create(ctypes.byref(h), dims, self.prec, int(self._normalize), float(self._scale),
+                                               int(self._fast_math), self.device, self.rank, G,
+                                               self.chunks if self.chunks > 1 else 0, self.z_chunks,
+                                               self.exchange_ctas_per_sm if G > 1 else 0))
+        self._native = h
+        geo = (ctypes.c_int64 * 8)()
+        self._check(lib.b2fft_slab_plan_geometry(h, geo))
+        self.chunks, self.z_chunks = int(geo[2]), int(geo[3])
+        sb, xb, fb = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(lib.b2fft_slab_plan_sizes(h, ctypes.byref(sb), ctypes.byref(xb), ctypes.byref(fb)))
         Xb = L["Xb"]
-        C = self.chunks if self.chunks > 1 else min(8, Y)
-        while Y % C:
-            C -= 1
-        self.chunks = C
-        Yc = Y // C
-        self._slab_buf = _DeviceBuffer(L["slab_elems"] * self.esz, self.device)
-        self._yslab_buf = _DeviceBuffer(L["xslab_elems"] * self.esz, self.device)
+        self._slab_buf = _DeviceBuffer(sb.value, self.device)
+        self._yslab_buf = _DeviceBuffer(xb.value, self.device)
+        self._flag_buf = _DeviceBuffer(max(fb.value, 256), self.device)
         self.slab = self._slab_buf.tensor(self.tdtype).view(Zl, Y, X)
         self.xslab = self._yslab_buf.tensor(self.tdtype).view(Y, Z, Xb)
         self.yslab = self.xslab                    # the distributed output, whatever its layout
         if G > 1:
             hs = [None] * G
-            dist.all_gather_object(hs, self._yslab_buf.handle(), group=self.group)
-            self._peer_yslab = _open_peers(hs, self.rank, self._yslab_buf.ptr, self.device)
+            dist.all_gather_object(hs, (self._yslab_buf.handle(), self._flag_buf.handle()), group=self.group)
+            self._peer_yslab = _open_peers([x[0] for x in hs], self.rank, self._yslab_buf.ptr, self.device)
+            self._peer_flags = _open_peers([x[1] for x in hs], self.rank, self._flag_buf.ptr, self.device)
         else:
-            self._peer_yslab = [self._yslab_buf.ptr]
+            self._peer_yslab, self._peer_flags = [self._yslab_buf.ptr], [self._flag_buf.ptr]
         self._peer_slab = None
-        mk = self._make
-        self._fwd_y = mk((X, Y, Zl), _lib.AXIS_Y, 0)
-        self._x_plans, self._z_plans = [], []
-        for c in range(C):
-            px = mk((X, Yc, Zl), _lib.AXIS_X, 0)
-            ptrs = [p + ((c * Yc) * Z * Xb + L["xs_peer_offset"]) * self.esz for p in self._peer_yslab]
-            self._set_blocks(px, ptrs, 1, L["xs_out_stride_y"])
-            _lib.check(lib.b2fft_plan_set_outer_split(px, Yc, X, Y * X, L["xs_out_stride_y"], L["xs_out_stride_z"]))
-            if G > 1 and self.exchange_ctas_per_sm > 0:
-                _lib.check(lib.b2fft_plan_set_exchange_ctas(px, self.exchange_ctas_per_sm))
-            self._x_plans.append(px)
-            self._z_plans.append(mk((Xb, Z, Yc), _lib.AXIS_Y, 1))
-        self._chunk_plans = self._x_plans + self._z_plans + [self._fwd_y]
-        self._inv_z = mk((Xb, Z, Y), _lib.AXIS_Y, 0)
-        self._inv_xy = mk((X, Y, Zl), _lib.AXIS_X | _lib.AXIS_Y, 1)
-        self._sx = torch.cuda.Stream(device=self.device)
-        self._sz = torch.cuda.Stream(device=self.device, priority=-1)
-        self._events = [torch.cuda.Event() for _ in range(C)]
-        self._Yc = Yc
+        xs = (ctypes.c_void_p * G)(*self._peer_yslab)
+        fl = (ctypes.c_void_p * G)(*self._peer_flags)
+        self._check(lib.b2fft_slab_plan_attach(h, self._slab_buf.ptr, xs, fl))
+        if G > 1:
+            dist.barrier(group=self.group)         # every rank has cleared its flag words before anyone signals
+
+    def _check(self, rc):
+        if rc == _lib.OK:
+            return
+        msg = self._lib.b2fft_slab_last_error()
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        if rc == _lib.E_INVALID:
+            raise ValueError(msg)
+        if rc == _lib.E_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise RuntimeError("b2fft: " + msg)
 
     def _forward_xslab(self):
-        torch, L = self._torch, self.L
-        cur = torch.cuda.current_stream(self.device)
-        self._sync_ranks()                  # every rank is done with its previous x-slab contents
-        self._exec(self._fwd_y, self._slab_buf.ptr, self._slab_buf.ptr, 0)
-        self._sx.wait_stream(cur)
-        self._sz.wait_stream(cur)
-        row_bytes = L["X"] * self.esz
-        zchunk_bytes = self._Yc * L["Z"] * L["Xb"] * self.esz
-        for c in range(self.chunks):
-            with torch.cuda.stream(self._sx):
-                src = self._slab_buf.ptr + c * self._Yc * row_bytes
-                self._exec(self._x_plans[c], src, src, 0)          # output goes to the block pointers
-                self._sync_ranks()                                 # chunk c of every peer has landed here
-                self._events[c].record(self._sx)
-            with torch.cuda.stream(self._sz):
-                self._sz.wait_event(self._events[c])
-                ptr = self._yslab_buf.ptr + c * zchunk_bytes
-                self._exec(self._z_plans[c], ptr, ptr, 0)
-        cur.wait_stream(self._sx)
-        cur.wait_stream(self._sz)
+        stream = self._torch.cuda.current_stream(self.device)
+        self._check(self._lib.b2fft_slab_forward(self._native, _stream_handle(stream)))
         return self.xslab
 
     def _inverse_xslab(self):
-        """x-slabs -> z-slabs.  Not the timed direction: inverse Z pass in place, an all-to-all of
-        re-packed blocks (torch permute copies + NCCL), inverse X and Y passes."""
-        torch, dist, L, G = self._torch, self._dist, self.L, self.world
-        X, Y, Z, Zl, Xb = L["X"], L["Y"], L["Z"], L["Zl"], L["Xb"]
-        self._sync_ranks()
-        self._exec(self._inv_z, self._yslab_buf.ptr, self._yslab_buf.ptr, 1)
-        send = self.xslab.view(Y, G, Zl, Xb).permute(1, 2, 0, 3).contiguous()        # [g][zl][y][xl]
-        if G > 1:
-            recv = torch.empty_like(send)
-            dist.all_to_all_single(torch_real(recv), torch_real(send), group=self.group)
-        else:
-            recv = send
-        # recv[h][zl][y][xl] -> slab[zl][y][h*Xb + xl]
-        self.slab.view(Zl, Y, G, Xb).copy_(recv.permute(1, 2, 0, 3))
-        del send, recv
-        self._exec(self._inv_xy, self._slab_buf.ptr, self._slab_buf.ptr, 1)
+        """x-slabs -> z-slabs: inverse Z pass per y-chunk, then the X pass pulls every row's pieces from the ranks'
+        x-slabs over NVLink (source-blocked loads), then the local Y pass with the scale (csrc/slab.cu)."""
+        stream = self._torch.cuda.current_stream(self.device)
+        self._check(self._lib.b2fft_slab_inverse(self._native, _stream_handle(stream)))
         return self.slab
+
+    def status(self):
+        """0 = healthy; non-zero = a cross-rank wait timed out on this rank (synchronises the device)."""
+        if getattr(self, "_native", None) is None:
+            return 0
+        out = ctypes.c_int(0)
+        self._check(self._lib.b2fft_slab_plan_status(self._native, ctypes.byref(out)))
+        return out.value
+
+    def describe(self):
+        if getattr(self, "_native", None) is None:
+            return "exchange=%s" % self.exchange
+        buf = ctypes.create_string_buffer(2048)
+        self._check(self._lib.b2fft_slab_plan_describe(self._native, buf, len(buf)))
+        return buf.value.decode()
 
     # ------------------------------------------------------------------ helpers
     def _set_blocks(self, plan, ptrs, out_inner, out_outer_stride):
@@ -354,6 +349,8 @@ class SlabPlan(object):
 
     @property
     def launch_count(self):
+        if self._native is not None:
+            return int(self._lib.b2fft_slab_plan_launch_count(self._native))
         plans = [self._fwd_xy, self._fwd_z, self._inv_z, self._inv_xy] + list(getattr(self, "_chunk_plans", []))
         return sum(int(self._lib.b2fft_plan_launch_count(p)) for p in plans if p is not None)
 
@@ -409,6 +406,26 @@ class SlabPlan(object):
         return self.slab
 
     def close(self):
+        if getattr(self, "_native", None) is not None:
+            self._torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                self._dist.barrier(group=self.group)       # nobody still reads or writes a peer's buffers
+            self._lib.b2fft_slab_plan_destroy(self._native)
+            self._native = None
+            if self.world > 1:
+                for table in (self._peer_yslab, getattr(self, "_peer_flags", [])):
+                    for r, p in enumerate(table):
+                        if r != self.rank:
+                            self._lib.b2fft_ipc_release(p)
+                self._dist.barrier(group=self.group)       # peers have unmapped my buffers before I free them
+            self._peer_yslab = self._peer_flags = None
+            self.slab = self.yslab = self.xslab = None
+            for b in ("_slab_buf", "_yslab_buf", "_flag_buf"):
+                buf = getattr(self, b, None)
+                if buf is not None:
+                    buf.free()
+                    setattr(self, b, None)
+            return
         for p in ("_fwd_xy", "_fwd_z", "_inv_z", "_inv_xy"):
             h = getattr(self, p, None)
             if h is not None:

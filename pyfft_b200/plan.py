@@ -84,14 +84,27 @@ def _device_pointer(obj, what):
         pass
     cai = getattr(obj, "__cuda_array_interface__", None)
     if cai is not None:
-        nbytes = None
+        nbytes, npdt = None, None
         try:
-            nbytes = int(numpy.prod(cai["shape"])) * numpy.dtype(cai["typestr"]).itemsize
+            npdt = numpy.dtype(cai["typestr"])
+            nbytes = int(numpy.prod(cai["shape"])) * npdt.itemsize
         except Exception:
             pass
-        return int(cai["data"][0]), nbytes, None
-    if hasattr(obj, "gpudata"):
-        return int(obj.gpudata), getattr(obj, "nbytes", None), None
+        strides = cai.get("strides")
+        if strides is not None and npdt is not None:          # None means C-contiguous; anything else must equal it
+            expect, acc = [], npdt.itemsize
+            for dim in reversed(tuple(cai["shape"])):
+                expect.append(acc)
+                acc *= int(dim)
+            dense = all(int(d) <= 1 or int(st) == e for d, st, e in zip(reversed(tuple(cai["shape"])), reversed(tuple(strides)), expect))
+            if not dense:
+                raise ValueError("%s: array must be C-contiguous (strides %r for shape %r)" % (what, strides, cai["shape"]))
+        return int(cai["data"][0]), nbytes, npdt
+    if hasattr(obj, "gpudata"):                              # pycuda.gpuarray.GPUArray (pyfft/cuda.py:37-39)
+        flags = getattr(obj, "flags", None)
+        if flags is not None and not getattr(flags, "c_contiguous", True):
+            raise ValueError("%s: GPUArray must be C-contiguous" % what)
+        return int(obj.gpudata), getattr(obj, "nbytes", None), getattr(obj, "dtype", None)
     if hasattr(obj, "data_ptr"):
         return int(obj.data_ptr()), None, None
     if hasattr(obj, "ptr"):
@@ -182,10 +195,18 @@ class FFTPlan(object):
                              % (what, nbytes, need, self._xyz, batch))
         if tdtype is not None:
             import torch
-            want = {numpy.dtype(numpy.complex64): torch.complex64, numpy.dtype(numpy.float32): torch.float32,
-                    numpy.dtype(numpy.complex128): torch.complex128, numpy.dtype(numpy.float64): torch.float64}
-            if tdtype != want[self._dtype]:
-                raise TypeError("%s has dtype %s, the plan was created for %s" % (what, tdtype, self._dtype))
+            if isinstance(tdtype, torch.dtype):
+                want = {numpy.dtype(numpy.complex64): torch.complex64, numpy.dtype(numpy.float32): torch.float32,
+                        numpy.dtype(numpy.complex128): torch.complex128, numpy.dtype(numpy.float64): torch.float64}
+                if tdtype != want[self._dtype]:
+                    raise TypeError("%s has dtype %s, the plan was created for %s" % (what, tdtype, self._dtype))
+            else:                                    # numpy dtype of a CAI / GPUArray buffer; raw byte buffers are accepted
+                try:
+                    npdt = numpy.dtype(tdtype)
+                except TypeError:
+                    npdt = None
+                if npdt is not None and npdt.kind in "fc" and npdt != self._dtype:
+                    raise TypeError("%s has dtype %s, the plan was created for %s" % (what, npdt, self._dtype))
         return ptr
 
     def _ensure_workspace(self, batch, in_place):

@@ -262,6 +262,67 @@ static void check_xslab_rows(const char* name) {
     if (!ok) ++g_fail;
 }
 
+// The inverse x-slab exchange pass (csrc/slab.cu b2fft_slab_inverse): a contiguous-axis pass whose LOADS are
+// source-blocked -- piece h of row (z, y) comes from buffer h at [(y*Z + zoff + z)*Xb + xl] -- walked through the
+// two-level outer index, with plain stores into the z-slab [Zl][Y][X].  Parameters as api.cu / slab.cu set them.
+template <class Cfg>
+static void check_xslab_pull_rows(const char* name) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    const int X = Cfg::N, G = 4, Xb = X / G;
+    if (Cfg::W != 1 || X % G) return;
+    const int Zl = 3, Y = 8, C = 2, Yc = Y / C, Z = Zl * G, zoff = 2 * Zl;      // "rank 2" of 4
+    std::mt19937_64 rng(123);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<std::vector<T2>> xs(G, std::vector<T2>((size_t)Y * Z * Xb));
+    for (auto& b : xs) for (auto& v : b) { v.x = (T)nd(rng); v.y = (T)nd(rng); }
+    std::vector<T2> slab((size_t)Zl * Y * X);
+    for (auto& v : slab) { v.x = NAN; v.y = NAN; }
+    std::vector<std::vector<T2>> tabs;
+    for (int s = 0; s + 1 < Cfg::S; ++s) tabs.push_back(make_stage_table<T>(Cfg::NS(s), Cfg::R(s)));
+    for (int c = 0; c < C; ++c) {
+        PassParams<T> p{};
+        for (int s = 0; s + 1 < Cfg::S; ++s) p.tw[s] = reinterpret_cast<const T*>(tabs[s].data());
+        p.out0 = reinterpret_cast<T*>(slab.data() + (size_t)c * Yc * X);
+        p.inner = 1; p.inner_blocks = 1;
+        p.n_tiles = (long long)Yc * Zl;
+        p.out_inner = 1;
+        p.out_blk_log2 = -1;
+        p.in_blk_log2 = ilog2(Xb);
+        for (int h = 0; h < G; ++h) p.in_blk[h] = reinterpret_cast<const T*>(xs[h].data() + ((size_t)c * Yc * Z + zoff) * Xb);
+        p.outer_div = Yc; p.outer_stride = (long long)Z * Xb; p.in_stride_hi = Xb;
+        p.out_outer_stride = X; p.out_stride_hi = (long long)Y * X;
+        p.scale = 1; p.scale_mode = 0;
+        const long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+        std::vector<T2> smem((size_t)Cfg::COL_SMEM * Cfg::W * Cfg::G + 1);
+        for (long long bid = 0; bid < ctas; ++bid) {
+            std::vector<TileThread<Cfg, false, true>> th(Cfg::THREADS);
+            for (int tid = 0; tid < Cfg::THREADS; ++tid) { th[tid].setup(tid, bid, p); th[tid].load(p); }
+            emu_stages<Cfg, false, true, 0>(th, p, smem);
+            for (auto& t : th) t.store(p);
+        }
+    }
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(X);
+    for (int z = 0; z < Zl; ++z)
+        for (int y = 0; y < Y; ++y) {
+            for (int x = 0; x < X; ++x) { auto v = xs[x / Xb][((size_t)y * Z + zoff + z) * Xb + x % Xb]; line[x] = cld(v.y, v.x); }   // inverse via swap
+            ref_fft(line);
+            for (int x = 0; x < X; ++x) {
+                const T2 g = slab[((size_t)z * Y + y) * X + x];
+                double e = (double)std::abs(cld(g.x, g.y) - cld(line[x].imag(), line[x].real()));
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(line[x]);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    const double tol = sizeof(T) == 4 ? 3e-6 : 1e-14;
+    const bool ok = max_err / max_mag < tol;
+    std::printf("%-44s x-slab inverse rows (source-blocked loads, outer split) err=%.2e %s\n", name, max_err / max_mag, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 template <class Cfg>
 static void check(const char* name, long long outer, long long inner) {
     using T = typename Cfg::T;
@@ -405,6 +466,106 @@ static void check_fourstep(const char* name) {
     if (!ok) ++g_fail;
 }
 
+// The fused two-step strided kernel (kernels.cuh fused2_fft_kernel): per super-tile, step A sub-tiles into the
+// CTA's scratch slot, then step B sub-tiles out of it, with the parameters VariantOpsFused2::launch builds.
+// `grid` CTAs stride over the super-tiles (slot reuse is exercised); in_place: out == in.
+template <class CfgA, class CfgB, bool INV>
+static double run_fused2(long long outer, long long inner, int grid, bool in_place, unsigned seed) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, N = N1 * N2;
+    const long long total = outer * N * inner;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T2> in_c(total), out_c(total), ref_in(total);
+    for (long long i = 0; i < total; ++i) { in_c[i].x = (T)nd(rng); in_c[i].y = (T)nd(rng); out_c[i].x = NAN; out_c[i].y = NAN; }
+    ref_in = in_c;
+    std::vector<T2> scratch((size_t)grid * N * W);
+    for (auto& v : scratch) { v.x = NAN; v.y = NAN; }
+    std::vector<std::vector<T2>> ta, tb;
+    for (int s = 0; s + 1 < CfgA::S; ++s) ta.push_back(make_stage_table<T>(CfgA::NS(s), CfgA::R(s)));
+    for (int s = 0; s + 1 < CfgB::S; ++s) tb.push_back(make_stage_table<T>(CfgB::NS(s), CfgB::R(s)));
+    auto t1 = make_fs_table<T>(N, N2, CfgA::TPC, 1), t2 = make_fs_table<T>(N, N2, CfgA::E, CfgA::TPC);
+    PassParams<T> p{};
+    p.in0 = reinterpret_cast<const T*>(in_c.data());
+    p.out0 = reinterpret_cast<T*>(in_place ? in_c.data() : out_c.data());
+    p.inner = inner; p.inner_blocks = inner / W; p.outer_stride = (long long)N * inner;
+    p.n_tiles = outer * p.inner_blocks;
+    p.out_inner = inner; p.out_outer_stride = p.outer_stride; p.out_blk_log2 = -1;
+    p.scale = (T)0.5; p.scale_mode = 1;
+    p.fs_t1 = reinterpret_cast<const T*>(t1.data()); p.fs_t2 = reinterpret_cast<const T*>(t2.data());
+    for (int s = 0; s + 1 < CfgA::S; ++s) p.tw[s] = reinterpret_cast<const T*>(ta[s].data());
+    for (int s = 0; s + 1 < CfgB::S; ++s) p.tw_b[s] = reinterpret_cast<const T*>(tb[s].data());
+    p.scratch = reinterpret_cast<T*>(scratch.data());
+    // ---- as VariantOpsFused2::launch
+    PassParams<T> pa = p, pb = p;
+    pa.inner = (long long)N2 * p.inner; pa.out0 = p.scratch; pa.out_inner = W; pa.scale_mode = 0; pa.fs_n2 = N2;
+    pb.in0 = p.scratch; pb.inner = (long long)N1 * W; pb.out_inner = (long long)N1 * p.out_inner;
+    for (int s = 0; s < 3; ++s) pb.tw[s] = p.tw_b[s];
+    pb.fs_t1 = pb.fs_t2 = nullptr;
+    std::vector<T2> smem((size_t)(CfgA::COL_SMEM * CfgA::G > CfgB::COL_SMEM * CfgB::G ? CfgA::COL_SMEM * CfgA::G : CfgB::COL_SMEM * CfgB::G) * W + 1);
+    for (int bid = 0; bid < grid; ++bid) {
+        const long long slot = (long long)bid * N * W;
+        for (long long sidx = bid; sidx < pa.n_tiles; sidx += grid) {
+            const long long o = sidx / pa.inner_blocks, ib = sidx - o * pa.inner_blocks;
+            for (int c = 0; c < N2 / CfgA::G; ++c) {
+                std::vector<TileThread<CfgA, false, INV, true>> th(CfgA::THREADS);
+                for (int tid = 0; tid < CfgA::THREADS; ++tid) {
+                    fused2_setup_a<CfgA, CfgB>(th[tid], tid, c, o * pa.outer_stride + ib * W, p.inner, slot);
+                    th[tid].load(pa);
+                }
+                emu_stages<CfgA, false, INV, 0>(th, pa, smem);
+                for (auto& t : th) t.store(pa);
+            }
+            for (int c = 0; c < N1 / CfgB::G; ++c) {
+                std::vector<TileThread<CfgB, false, INV, false>> th(CfgB::THREADS);
+                for (int tid = 0; tid < CfgB::THREADS; ++tid) {
+                    fused2_setup_b<CfgA, CfgB>(th[tid], tid, c, o * pb.out_outer_stride + ib * W, p.out_inner, slot);
+                    th[tid].load(pb);
+                }
+                emu_stages<CfgB, false, INV, 0>(th, pb, smem);
+                for (auto& t : th) t.store(pb);
+            }
+            for (long long i = 0; i < (long long)N * W; ++i) { scratch[slot + i].x = NAN; scratch[slot + i].y = NAN; }   // poison
+        }
+    }
+    const std::vector<T2>& got_c = in_place ? in_c : out_c;
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner; ++i) {
+            for (long long n = 0; n < N; ++n) {
+                const T2 v = ref_in[(o * N + n) * inner + i];
+                line[n] = INV ? cld(v.y, v.x) : cld(v.x, v.y);
+            }
+            ref_fft(line);
+            for (long long n = 0; n < N; ++n) {
+                cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+                want *= 0.5L;
+                const T2 g = got_c[(o * N + n) * inner + i];
+                double e = (double)std::abs(cld(g.x, g.y) - want);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(want);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <class CfgA, class CfgB>
+static void check_fused2(const char* name) {
+    using T = typename CfgA::T;
+    const double tol = sizeof(T) == 4 ? 4e-6 : 2e-14;
+    static_assert(CfgA::THREADS == CfgB::THREADS && CfgA::W == CfgB::W, "fused steps share the CTA shape");
+    double e0 = run_fused2<CfgA, CfgB, false>(1, 3 * CfgA::W, 2, false, 21);
+    double e1 = run_fused2<CfgA, CfgB, true>(2, CfgA::W, 1, true, 22);
+    bool ok = e0 < tol && e1 < tol;
+    std::printf("%-44s fused two-step N=%dx%d  err fwd(oop)=%.2e inv(in place)=%.2e thr=%d %s\n", name, CfgA::N, CfgB::N, e0, e1,
+                CfgA::THREADS, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 #define CHKT(T, L, G, R0, R1, R2, R3) \
     check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
 
@@ -416,7 +577,8 @@ static void check_fourstep(const char* name) {
     if ((W) > 1 && (L) >= 3) check_blocked<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3, OUTER, INNER, (L) >= 8 ? 8 : 2);
 
 #define CHKXS(T, L, W, G, R0, R1, R2, R3) \
-    check_xslab_rows<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3);
+    check_xslab_rows<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3); \
+    check_xslab_pull_rows<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3);
 
 #define CHKF(T, L, W, G, R0, R1, R2, R3) \
     check_fourstep<TileCfg<T, L, W, G, R0, R1, R2, R3>>(#T " n" #L " w" #W " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3);

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_slab_plan_single_rank(cuda_device, shape, dtype, layout):
     import torch
     from pyfft_b200.dist import SlabPlan
-    plan = SlabPlan(shape, dtype=dtype, yslab_layout=layout)
+    plan = SlabPlan(shape, dtype=dtype, exchange="p2p", yslab_layout=layout)
     x = no.make_input(shape, 1, dtype, seed=9)[0]
     plan.slab.copy_(torch.from_numpy(x).to(cuda_device))
     y = plan.forward()
@@ -37,15 +37,17 @@ def test_slab_plan_single_rank(cuda_device, shape, dtype, layout):
     plan.close()
 
 
-@pytest.mark.parametrize("chunks", [1, 4])
+@pytest.mark.parametrize("chunks,z_chunks", [(1, 1), (4, 1), (4, 2), (8, 4)])
 @pytest.mark.parametrize("shape,dtype", [((32, 64, 128), np.complex64), ((64, 32, 32), np.complex128), ((256, 256, 256), np.complex64),
-                                         ((16, 8, 2048), np.complex64)])
-def test_xslab_plan_single_rank(cuda_device, shape, dtype, chunks):
-    """x-slab exchange mode on one rank: Y pass, chunked X pass with destination-blocked stores through
-    the two-level outer index (b2fft_plan_set_outer_split), chunked Z pass on the [Y][Z][X] result."""
+                                         ((16, 8, 2048), np.complex64), ((4096, 8, 64), np.complex64)])
+def test_xslab_plan_single_rank(cuda_device, shape, dtype, chunks, z_chunks):
+    """The native slab plan (b2fft_slab_*, csrc/slab.cu) on one rank: Y pass per z-chunk, chunked X pass with
+    destination-blocked stores through the two-level outer index, chunked Z pass on the [Y][Z][X] result (the last
+    shape has a 4096-long Z axis: its sub-plan needs the plan-owned workspace); inverse with source-blocked loads."""
     import torch
     from pyfft_b200.dist import SlabPlan
-    plan = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=chunks)
+    plan = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=chunks, z_chunks=z_chunks)
+    assert plan.status() == 0 and "x-slab" in plan.describe()
     x = no.make_input(shape, 1, dtype, seed=19)[0]
     plan.slab.copy_(torch.from_numpy(x).to(cuda_device))
     y = plan.forward()
@@ -56,6 +58,10 @@ def test_xslab_plan_single_rank(cuda_device, shape, dtype, chunks):
     back = plan.inverse()
     torch.cuda.synchronize()
     assert no.rel_l2(back.cpu().numpy(), x) < tol
+    y2 = plan.forward()                      # a second round trip reuses the flag words / epochs
+    torch.cuda.synchronize()
+    assert no.rel_l2(y2.cpu().numpy().transpose(1, 0, 2), want) < tol
+    assert plan.status() == 0 and plan.launch_count > 0
     plan.close()
 
 
@@ -75,10 +81,10 @@ def test_slab_two_ranks_if_available(cuda_device):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "slab_check.py"), "--size", "64", "128",
-           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx", "ncclx4", "xslab", "xslabx2"]
+           "--check", "--steps", "0", "--exchange", "p2p", "nccl", "p2p-yzx", "ncclx4", "xslab", "xslabx2", "xslabx4z2"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     recs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
-    assert len(recs) == 12
+    assert len(recs) == 14
     for r in recs:
         assert r["fwd_rel_l2"] < 1e-5 * 21 and r["roundtrip_rel_l2"] < 1e-5 * 21 and r["delta_max_err"] < 1e-4, r

@@ -74,3 +74,48 @@ def test_stream_handles():
     assert _stream_handle(_Ptr(99)) == 99
     with pytest.raises(TypeError):
         _stream_handle(object())
+
+
+class _CaiView(object):             # non-contiguous CuPy-style view: strides given explicitly
+    def __init__(self, ptr, shape, strides, typestr="<c8"):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": strides}
+
+
+class _Flags(object):
+    def __init__(self, c):
+        self.c_contiguous = c
+
+
+def test_noncontiguous_buffers_are_refused():
+    # dense strides written out explicitly are fine, views with gaps are not (they would be transformed as if dense)
+    assert _device_pointer(_CaiView(4096, (4, 8), (64, 8)), "x")[:2] == (4096, 256)
+    assert _device_pointer(_CaiView(4096, (1, 8), (640, 8)), "x")[0] == 4096           # size-1 axes: any stride
+    with pytest.raises(ValueError):
+        _device_pointer(_CaiView(4096, (4, 8), (128, 8)), "x")
+    with pytest.raises(ValueError):
+        _device_pointer(_CaiView(4096, (4, 8), (64, 16)), "x")
+    ga = _GpuArray(8192, 64)
+    ga.flags = _Flags(False)
+    with pytest.raises(ValueError):
+        _device_pointer(ga, "x")
+    ga.flags = _Flags(True)
+    assert _device_pointer(ga, "x")[0] == 8192
+
+
+def test_context_selector_must_be_understood():
+    """`context=` objects that do not identify a device raise instead of silently meaning 'current device'."""
+    from pyfft_b200 import cuda as b2cuda
+
+    class _Dev(object):
+        pass
+
+    class _Ctx(object):
+        def get_device(self):
+            return _Dev()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            b2cuda._device_of(_Ctx(), None)
+        return
+    with pytest.raises(ValueError):
+        b2cuda._device_of(_Ctx(), None)

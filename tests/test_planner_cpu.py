@@ -63,10 +63,18 @@ def test_layout_and_pitch_aware_variant_choice(built_lib):
     # split-layout rows take the TMA-staged kernel, interleaved rows the plain high-occupancy one
     assert "_tma" in _preview(built_lib, 4096, layout=1)[0]["variant"]
     assert "_tma" not in _preview(built_lib, 4096, layout=0)[0]["variant"]
-    # strided axes: TMA tensor staging for N >= 1024 unless rows are >= 256 KiB apart
+    # strided axes: TMA tensor staging for N >= 1024 while rows are < 256 KiB apart ...
     assert "_tmac" in _preview(built_lib, 1024, 1024)[1]["variant"]
+    assert "_tmac" in _preview(built_lib, 2048, 2048, 2048)[1]["variant"]
+    # ... and the fused two-step kernel (128-byte pieces on both DRAM sides) beyond, in both precisions,
     z = _preview(built_lib, 2048, 2048, 2048)[2]
-    assert "_tmac" not in z["variant"] and "_w8_" in z["variant"]
+    assert "_fused2" in z["variant"] and "_w16_" in z["variant"]
+    assert "_fused2" in _preview(built_lib, 1024, 1024, 1024)[2]["variant"]
+    assert "_fused2" in _preview(built_lib, 256, 64, 1024, prec=1)[2]["variant"]
+    # ... unless the layout is split or the inner stride is not a multiple of 128 bytes: widest plain tile
+    z = _preview(built_lib, 2048, 2048, 2048, layout=1)[2]
+    assert "_fused2" not in z["variant"] and "_tmac" not in z["variant"] and "_w8_" in z["variant"]
+    assert "_fused2" not in _preview(built_lib, 8, 8192, 2048)[2]["variant"]
 
 
 def test_preview_validation(built_lib):

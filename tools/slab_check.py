@@ -49,8 +49,12 @@ def main():
                 continue
             yzx = ex.endswith("-yzx")
             chunks = int(ex.split("x")[1]) if ex.startswith("ncclx") else 1          # "ncclx8" = 8 pipelined chunks
-            xs = ex.startswith("xslab")               # "xslab" / "xslabx4" = 4 y-chunks / "xslabx8c1" = 1 exchange CTA per SM
-            ctas = 2
+            xs = ex.startswith("xslab")               # "xslab" / "xslabx4" = 4 y-chunks / "xslabx8c1" = 1 exchange CTA per SM / "xslabx8z2" = 2 z-chunks
+            ctas = 3
+            zch = 1
+            if xs and "z" in ex[5:]:
+                ex, _, zz = ex.rpartition("z")
+                zch = int(zz)
             if xs and "c" in ex[5:]:
                 ex_, _, cc = ex.rpartition("c")
                 ctas = int(cc)
@@ -59,7 +63,7 @@ def main():
             if xs and "x" in ex_[5:]:
                 chunks = int(ex_[5:].split("x")[1])
             plan = SlabPlan(shape, dtype=npdt, exchange="xslab" if xs else "nccl" if ex.startswith("nccl") else ex.split("-")[0],
-                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas)
+                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas, z_chunks=zch)
             L = plan.L
             g = torch.Generator(device=dev)
             g.manual_seed(4242 + rank)
@@ -70,7 +74,8 @@ def main():
                 for z0 in range(0, L["Zl"], zs):          # in pieces: no slab-sized temporaries
                     z1 = min(L["Zl"], z0 + zs)
                     plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, n, n, 2, dtype=fl, device=dev, generator=g)))
-            rec = {"n": n, "world": world, "exchange": ex, "dtype": args.dtype}
+            rec = {"n": n, "world": world, "exchange": ex + ("z%d" % zch if zch > 1 else ""), "dtype": args.dtype,
+                   "y_chunks": plan.chunks, "z_chunks": getattr(plan, "z_chunks", 1)}
             fill()
             x_local = plan.slab.clone() if (args.check or n <= 1024) else None
             energy_in = float((plan.slab.abs() ** 2).sum().double().item())
@@ -148,6 +153,8 @@ def main():
                 rec["launches_per_step"] = (plan.launch_count - l0) / args.steps
                 rec["sent_bytes_per_gpu"] = L["slab_elems"] * npdt.itemsize * (world - 1) / world
                 rec["nvlink_gbs_per_gpu_if_exchange_were_all"] = rec["sent_bytes_per_gpu"] / (ms * 1e-3) / 1e9
+            if hasattr(plan, "status"):
+                rec["status"] = plan.status()
             plan.close()
             del plan
             torch.cuda.empty_cache()
