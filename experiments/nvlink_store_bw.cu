@@ -93,7 +93,7 @@ int main(int argc, char** argv) {
         CK(cudaEventSynchronize(e1));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        std::printf("%-28s ctas/sm=%-3d %8.1f GB/s\n", name, cap, bytes * (double)reps / (ms * 1e-3) / 1e9);
+        std::printf("%-30s ctas/sm=%-3d %8.1f GB/s\n", name, cap, bytes * (double)reps / (ms * 1e-3) / 1e9);
     };
     time("cudaMemcpyPeerAsync", 0, [&] { CK(cudaMemcpyPeerAsync(dst, 1, src, 0, bytes)); });
     time("local copy st.v4 (HBM)", 0, [&] { copy_st<4><<<sms * 8, 256>>>(src, loc, bytes / 16); });
@@ -102,6 +102,8 @@ int main(int argc, char** argv) {
         const int grid = cap ? sms * cap : sms * 16;
         time("peer st.v2 (8 B/thread)", cap, [&] { copy_st<2><<<grid, 256>>>(src, dst, bytes / 8); });
         time("peer st.v4 (16 B/thread)", cap, [&] { copy_st<4><<<grid, 256>>>(src, dst, bytes / 16); });
+        time("peer ld.v2 (pull, 8 B/thread)", cap, [&] { copy_st<2><<<grid, 256>>>(dst, loc, bytes / 8); });
+        time("peer ld.v4 (pull, 16 B/thr)", cap, [&] { copy_st<4><<<grid, 256>>>(dst, loc, bytes / 16); });
         const int ppc = 8;                                   // pieces per CTA and round
         const size_t smem = (size_t)ppc * piece;
         CK(cudaFuncSetAttribute(copy_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

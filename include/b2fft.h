@@ -174,6 +174,12 @@ B2FFT_API int b2fft_slab_inverse(b2fft_slab_plan* plan, void* cuda_stream);
 /* 0 = healthy; non-zero = a cross-rank wait timed out (a peer never signalled); synchronises the device */
 B2FFT_API int b2fft_slab_plan_status(b2fft_slab_plan* plan, int* out);
 B2FFT_API int64_t b2fft_slab_plan_launch_count(const b2fft_slab_plan* plan);
+/* Timeline of the exchange pipeline (measurement aid): with tracing on, b2fft_slab_forward records a timing event at
+ * every phase boundary; b2fft_slab_plan_trace synchronises the device and writes "name:ms;..." (completion time of the
+ * Y pass of z-chunk k, the X pass of (z-chunk, y-chunk), the arrival of y-chunk c from all peers, the Z pass of c),
+ * relative to the start of the last forward call. */
+B2FFT_API int b2fft_slab_plan_set_trace(b2fft_slab_plan* plan, int on);
+B2FFT_API int b2fft_slab_plan_trace(b2fft_slab_plan* plan, char* buf, size_t buflen);
 B2FFT_API int b2fft_slab_plan_describe(const b2fft_slab_plan* plan, char* buf, size_t buflen);
 B2FFT_API int b2fft_slab_plan_destroy(b2fft_slab_plan* plan);
 B2FFT_API const char* b2fft_slab_last_error(void);

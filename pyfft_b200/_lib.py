@@ -42,6 +42,8 @@ SIGNATURES = {
     "b2fft_slab_plan_status": (_i, [_vp, ctypes.POINTER(_i)]),
     "b2fft_slab_plan_launch_count": (_i64, [_vp]),
     "b2fft_slab_plan_describe": (_i, [_vp, ctypes.c_char_p, _sz]),
+    "b2fft_slab_plan_set_trace": (_i, [_vp, _i]),
+    "b2fft_slab_plan_trace": (_i, [_vp, ctypes.c_char_p, _sz]),
     "b2fft_slab_plan_destroy": (_i, [_vp]),
     "b2fft_slab_last_error": (ctypes.c_char_p, []),
     "b2fft_plan_set_outer_split": (_i, [_vp, _i64, _i64, _i64, _i64, _i64]),

@@ -584,8 +584,21 @@ struct TileThread {
     B2_HD void apply_fs_twiddle(const PassParams<T>& p) {
         constexpr int s = S - 1;
         constexpr int R = Cfg::R(s), LG = ilog2(R), BPT = Cfg::BPT(s);
-        const T2* t1p = reinterpret_cast<const T2*>(p.fs_t1) + (long long)t * p.fs_n2 + fs_n2i;
         const T2* t2p = reinterpret_cast<const T2*>(p.fs_t2) + fs_n2i;
+        if constexpr (TPC == 1) {
+            // one thread per column (t == 0): the first table is all ones, w_N^(k1*n2) is the second table's entry itself
+            static_for<0, BPT>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                static_for<0, R>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int q = i * R + brev(k, LG);
+                    constexpr int c = i + k * BPT;
+                    if constexpr (c > 0) v[q] = cmul<INV>(v[q], ld_c(t2p + (long long)c * p.fs_n2));
+                });
+            });
+            return;
+        }
+        const T2* t1p = reinterpret_cast<const T2*>(p.fs_t1) + (long long)t * p.fs_n2 + fs_n2i;
         const C b = ld_c(t1p);
         static_for<0, BPT>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
@@ -716,6 +729,37 @@ B2_HD void fused2_setup_b(TH& th, int tid, int c, long long out_base, long long 
     th.fs_n2i = 0;
     th.base = slot + k1 * W + th.w;                        // element n2 at + n2 * (N1*W)
     th.obase = out_base + k1 * inner_out + th.w;           // output k = k1 + N1*k2 at + k2 * (N1*inner_out)
+}
+
+// ---- shared-memory-resident variant (kernels.cuh fused2s_fft_kernel): both steps are single-stage register FFTs
+// (CfgA::S == CfgB::S == 1, one column per thread), so the CTA needs no exchange buffer and the intermediate of the
+// super-tile itself lives in shared memory, laid out [k1][n2][W]; only the rows k1 >= KS that do not fit go through the
+// (then tiny) global scratch slot, laid out [k1 - KS][n2][W].
+template <class CfgA, class CfgB, int KS, class TH>
+B2_HD void fused2s_store_a(const TH& th, vec2<typename CfgA::T>* smem_i, vec2<typename CfgA::T>* scratch_slot,
+                           unsigned long long pol) {
+    static_assert(CfgA::S == 1 && CfgA::TPC == 1, "step A is one register FFT per thread");
+    constexpr int R = CfgA::E, LG = ilog2(R), W = CfgA::W, N2 = CfgB::N;
+    const long long n2 = th.fs_n2i;
+    static_for<0, R>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;             // k1
+        constexpr int q = brev(k, LG);
+        if constexpr (k < KS) st_c(smem_i + ((long long)k * N2 + n2) * W + th.w, th.v[q]);
+        else st_c_pol(scratch_slot + ((long long)(k - KS) * N2 + n2) * W + th.w, th.v[q], pol);
+    });
+}
+template <class CfgA, class CfgB, int KS, class TH>
+B2_HD void fused2s_load_b(TH& th, int k1, const vec2<typename CfgA::T>* smem_i, const vec2<typename CfgA::T>* scratch_slot,
+                          unsigned long long pol) {
+    static_assert(CfgB::S == 1 && CfgB::TPC == 1, "step B is one register FFT per thread");
+    constexpr int W = CfgA::W, N2 = CfgB::N;
+    if (k1 < KS) {
+        const vec2<typename CfgA::T>* src = smem_i + (long long)k1 * N2 * W + th.w;
+        static_for<0, N2>([&](auto jc) { th.v[decltype(jc)::value] = ld_c(src + decltype(jc)::value * W); });
+    } else {
+        const vec2<typename CfgA::T>* src = scratch_slot + (long long)(k1 - KS) * N2 * W + th.w;
+        static_for<0, N2>([&](auto jc) { th.v[decltype(jc)::value] = ld_stream_c_pol(src + decltype(jc)::value * W, pol); });
+    }
 }
 
 }  // namespace b2

@@ -596,6 +596,80 @@ fused2_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, const
     }
 }
 
+
+// ------------------------------------------------------------------ fused two-step strided kernel, intermediate in shared memory
+// Same decomposition as fused2_fft_kernel, for N = E_A * E_B with both steps done as single register FFTs (radix-32 and
+// radix-64 for N = 2048): no exchange buffer is needed, so the [k1][n2][W] intermediate of the 128-byte-wide super-tile
+// occupies the CTA's shared memory (KS of the N1 rows k1; the rest -- 1/8 of it for N = 2048 -- goes through a 32 KiB
+// global scratch slot per CTA, 5 MB in total, which does stay in L2).  The L2-scratch version above loses 35-45 % of its
+// DRAM bandwidth to write-backs and re-reads of the 38-76 MB scratch (profiles/r02_fused2.md); here DRAM sees one read and
+// one write per element.  One CTA per SM: the loads of the next step-A sub-tile are issued into a second register set
+// before the current one is transformed, so HBM latency hides behind the butterflies.
+template <class CfgA, class CfgB, int KS, bool INV>
+__global__ void __launch_bounds__(CfgA::THREADS, 1)
+fused2s_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, const __grid_constant__ PassParams<typename CfgA::T> pb,
+                   const long long inner_in, const long long inner_out) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    static_assert(CfgA::THREADS == CfgB::THREADS && CfgA::W == CfgB::W, "both steps run on the same CTA shape");
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N;
+    static_assert(N2 % CfgA::G == 0 && N1 % CfgB::G == 0 && KS <= N1 && (KS % 2) == 0, "sub-tiles must divide the super-tile");
+    constexpr int NSA = N2 / CfgA::G, NSB = N1 / CfgB::G;
+    extern __shared__ __align__(16) unsigned char b2_smem_raw[];
+    T2* smem_i = reinterpret_cast<T2*>(b2_smem_raw);
+    const int tid = (int)threadIdx.x;
+    T2* scratch_slot = reinterpret_cast<T2*>(pa.out0) + (long long)blockIdx.x * ((long long)(N1 - KS) * N2 * W);
+    unsigned long long pol_stream, pol_scratch;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_scratch));
+    using THA = TileThread<CfgA, false, INV, true, true>;
+    for (long long s = blockIdx.x; s < pa.n_tiles; s += gridDim.x) {
+        const long long o = s / pa.inner_blocks, ib = s - o * pa.inner_blocks;
+        const long long in_base = o * pa.outer_stride + ib * W;
+        {
+            THA ta, tb;
+            ta.pol_in = tb.pol_in = pol_stream;
+            fused2_setup_a<CfgA, CfgB>(ta, tid, 0, in_base, inner_in, 0);
+            ta.load(pa);
+            static_for<0, NSA>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                THA& cur = (c % 2 == 0) ? ta : tb;
+                THA& nxt = (c % 2 == 0) ? tb : ta;
+                if constexpr (c + 1 < NSA) {
+                    fused2_setup_a<CfgA, CfgB>(nxt, tid, c + 1, in_base, inner_in, 0);
+                    nxt.load(pa);
+                }
+                cur.template compute<0>(pa);
+                cur.apply_fs_twiddle(pa);
+                fused2s_store_a<CfgA, CfgB, KS>(cur, smem_i, scratch_slot, pol_scratch);
+            });
+        }
+        __syncthreads();                                         // the whole intermediate is in place
+        {
+            const long long s2 = s + gridDim.x;                  // first step-A sub-tile of this CTA's next super-tile -> L2
+            if (s2 < pa.n_tiles) {
+                const long long o2 = s2 / pa.inner_blocks, ib2 = s2 - o2 * pa.inner_blocks;
+                const T2* nb = reinterpret_cast<const T2*>(pa.in0) + o2 * pa.outer_stride + ib2 * W;
+                for (int r = tid; r < N1 * CfgA::G; r += CfgA::THREADS)      // rows n1*N2 + n2, n2 < GA
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + ((long long)(r / CfgA::G) * N2 + (r % CfgA::G)) * inner_in));
+            }
+        }
+        {
+            TileThread<CfgB, false, INV, false, true> th;
+            th.pol_out = pol_stream;
+            const long long out_base = o * pb.out_outer_stride + ib * W;
+#pragma unroll 1
+            for (int c = 0; c < NSB; ++c) {
+                fused2_setup_b<CfgA, CfgB>(th, tid, c, out_base, inner_out, 0);
+                fused2s_load_b<CfgA, CfgB, KS>(th, c * CfgB::G + th.g, smem_i, scratch_slot, pol_scratch);
+                th.template compute<0>(pb);
+                th.store(pb);
+            }
+        }
+        __syncthreads();                                         // intermediate fully read before the next super-tile overwrites it
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -1054,6 +1128,84 @@ struct VariantOpsFused2 {
     }
 };
 
+
+template <class CfgA, class CfgB, int KS>
+struct VariantOpsFused2S {
+    using T = typename CfgA::T;
+    static constexpr size_t SMEM = (size_t)KS * CfgB::N * CfgA::W * 2 * sizeof(T);
+    static_assert(SMEM <= 227 * 1024, "intermediate rows kept in shared memory must fit");
+    static int& slots() { static int s = 0; return s; }
+    static cudaError_t prepare() {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(fused2s_fft_kernel<CfgA, CfgB, KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(fused2s_fft_kernel<CfgA, CfgB, KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM)) != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused2s_fft_kernel<CfgA, CfgB, KS, false>, CfgA::THREADS, SMEM);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return cudaSuccess;
+    }
+    static int grid_slots() {
+        if (slots() <= 0 && prepare() != cudaSuccess) return -1;
+        return slots();
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        if (split || p.out_blk_log2 >= 0 || p.outer_div > 0 || !p.scratch || !p.fs_t2) return cudaErrorNotSupported;
+        if (p.n_tiles <= 0) return cudaSuccess;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        long long ctas = p.n_tiles;
+        if (ctas > slots()) ctas = slots();
+        if (ctas > p.scratch_slots) ctas = p.scratch_slots;
+        if (p.max_ctas > 0 && ctas > p.max_ctas) ctas = p.max_ctas;
+        if (ctas <= 0) return cudaErrorInvalidValue;
+        PassParams<T> pa = p, pb = p;
+        pa.inner = (long long)CfgB::N * p.inner;          // n1 stride
+        pa.out0 = p.scratch;
+        pa.scale_mode = 0;
+        pa.fs_n2 = CfgB::N;
+        pb.in0 = p.scratch;
+        pb.out_inner = (long long)CfgA::N * p.out_inner;  // k2 stride in the output
+        pb.fs_t1 = pb.fs_t2 = nullptr;
+        const dim3 grid((unsigned)ctas), block(CfgA::THREADS);
+        if (inv) fused2s_fft_kernel<CfgA, CfgB, KS, true><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        else fused2s_fft_kernel<CfgA, CfgB, KS, false><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused2s_fft_kernel<CfgA, CfgB, KS, false>, CfgA::THREADS, SMEM) !=
+            cudaSuccess)
+            return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v{};
+        v.name = name;
+        v.prec = sizeof(T) == 4 ? 0 : 1;
+        v.log2n = CfgA::LOG2N + CfgB::LOG2N;
+        v.log2n1 = CfgA::LOG2N;
+        v.W = CfgA::W; v.G = CfgA::G; v.E = CfgA::E; v.S = 1;
+        v.S_b = 1; v.E_b = CfgB::E;
+        for (int s = 0; s < 4; ++s) { v.radix[s] = s == 0 ? CfgA::E : 1; v.radix_b[s] = s == 0 ? CfgB::E : 1; }
+        v.threads = CfgA::THREADS;
+        v.smem_bytes = (long long)SMEM;
+        v.minb = 1;
+        v.kind = 3;
+        v.slot_elems = (long long)(CfgA::N - KS) * CfgB::N * CfgA::W;
+        if (v.slot_elems == 0) v.slot_elems = CfgA::W;          // keep a (dummy) scratch allocation so that launch() runs
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        v.grid_slots = &grid_slots;
+        return v;
+    }
+};
+
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x
 #define B2_STR(x) B2_STR2(x)
@@ -1107,6 +1259,13 @@ struct VariantOpsFused2 {
     out.push_back(::b2::VariantOpsFused2<::b2::TileCfg<T, L1, W, GA, A0, A1, A2, A3>,                  \
                                          ::b2::TileCfg<T, L2, W, GB, B0, B1, B2_, B3>, MB>::make(      \
         #T "_n" B2_STR(L1) "+" B2_STR(L2) "_w" B2_STR(W) "_g" B2_STR(GA) "+" B2_STR(GB) "_b" B2_STR(MB) "_r" B2_STR(A0) "x" B2_STR(A1) "x" B2_STR(A2) "+" B2_STR(B0) "x" B2_STR(B1) "x" B2_STR(B2_) "_fused2"));
+
+// B2_VS(type, log2n1, log2n2, W, GA, GB, KS): fused two-step strided variant with the intermediate in shared memory; step A
+// is a radix-2^log2n1 register FFT per thread (GA values of n2 per sub-tile), step B a radix-2^log2n2 one (GB values of k1)
+#define B2_VS(T, L1, L2, W, GA, GB, KS)                                                              \
+    out.push_back(::b2::VariantOpsFused2S<::b2::TileCfg<T, L1, W, GA, (1 << L1)>,                     \
+                                          ::b2::TileCfg<T, L2, W, GB, (1 << L2)>, KS>::make(          \
+        #T "_n" B2_STR(L1) "+" B2_STR(L2) "_w" B2_STR(W) "_g" B2_STR(GA) "+" B2_STR(GB) "_ks" B2_STR(KS) "_fused2s"));
 
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);

@@ -116,6 +116,22 @@ struct b2fft_slab_plan {
     unsigned epoch = 0;                   // one per forward / inverse call
     unsigned last_inverse_epoch = 0;      // peers pulled from my x-slab during that call
     bool attached = false;
+    // optional timeline of the last forward call (b2fft_slab_plan_set_trace): timing events at the phase boundaries
+    bool trace = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(const char* what, int a, int b, cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, st);
+        char nm[64];
+        snprintf(nm, sizeof nm, b >= 0 ? "%s[%d,%d]" : a >= 0 ? "%s[%d]" : "%s", what, a, b);
+        marks.emplace_back(nm, ev);
+    }
+    void clear_marks() {
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
     long long timeout_cycles = 20LL * 1000 * 1000 * 1000;   // ~10 s at 2 GHz
     // flag word layout (each word written by exactly one remote rank)
     int w_ready(int src) const { return src; }
@@ -261,6 +277,8 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     const size_t esz = sp->esz;
     const int G = sp->G, C = sp->C, K = sp->K;
     ++sp->epoch;
+    sp->clear_marks();
+    sp->mark("start", -1, -1, s);
     if (G > 1) {
         // peers may still be pulling from my x-slab (previous inverse): wait for them, then tell everybody that my
         // x-slab may be overwritten (everything queued on `s` before this call has consumed it)
@@ -273,9 +291,10 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     for (int k = 0; k < K; ++k) {
         char* zk = sp->slab + (size_t)k * sp->Zk * sp->Y * sp->X * esz;
         SLAB_TRY(b2fft_execute(sp->fwd_y, zk, nullptr, zk, nullptr, 0, 1, s));
+        sp->mark("Y", k, -1, s);
         SLAB_CUDA(cudaEventRecord(sp->ev_y[k], s));
         SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[k], 0));
-        if (k == 0 && G > 1) SLAB_TRY(slab_wait(sp, sp->w_ready(0), 1, sp->epoch, sp->sx));
+        if (k == 0 && G > 1) { SLAB_TRY(slab_wait(sp, sp->w_ready(0), 1, sp->epoch, sp->sx)); sp->mark("peers_ready", -1, -1, sp->sx); }
         for (int c = 0; c < C; ++c) {
             // rows {z in chunk k} x {y in chunk c}: row (z, y) starts at slab[(z*Y + y)*X]; its x-block h goes to
             // xslab_h[(y*Z + rank*Zl + z)*Xb]
@@ -285,16 +304,19 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
             SLAB_TRY(b2fft_plan_set_output_blocks(sp->fwd_x, G, blk.data(), nullptr, 1, sp->Z * sp->Xb));
             SLAB_TRY(b2fft_plan_set_outer_split(sp->fwd_x, sp->Yc, sp->X, sp->Y * sp->X, sp->Z * sp->Xb, sp->Xb));
             SLAB_TRY(b2fft_execute(sp->fwd_x, src, nullptr, src, nullptr, 0, 1, sp->sx));
+            sp->mark("X", k, c, sp->sx);
             if (k == K - 1) {
                 if (G > 1) {
                     SLAB_TRY(slab_signal(sp, sp->w_chunk(sp->rank, c), sp->sx));
                     SLAB_TRY(slab_wait(sp, sp->w_chunk(0, c), C, sp->epoch, sp->sz));
+                    sp->mark("chunk_arrived", c, -1, sp->sz);
                 } else {
                     SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
                     SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_sx, 0));
                 }
                 char* zc = sp->xslab[sp->rank] + (size_t)c * sp->Yc * sp->Z * sp->Xb * esz;
                 SLAB_TRY(b2fft_execute(sp->fwd_z, zc, nullptr, zc, nullptr, 0, 1, sp->sz));
+                sp->mark("Z", c, -1, sp->sz);
             }
         }
     }
@@ -302,6 +324,32 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     SLAB_CUDA(cudaEventRecord(sp->ev_sz, sp->sz));
     SLAB_CUDA(cudaStreamWaitEvent(s, sp->ev_sx, 0));
     SLAB_CUDA(cudaStreamWaitEvent(s, sp->ev_sz, 0));
+    sp->mark("end", -1, -1, s);
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_set_trace(b2fft_slab_plan* sp, int on) {
+    if (!sp) return slab_fail(B2FFT_E_INVALID, "null plan");
+    sp->trace = on != 0;
+    if (!sp->trace) sp->clear_marks();
+    return B2FFT_OK;
+}
+
+/* "name:ms;name:ms;..." -- completion time of every phase of the last traced forward call, relative to its start.
+ * Synchronises the device. */
+int b2fft_slab_plan_trace(b2fft_slab_plan* sp, char* buf, size_t buflen) {
+    if (!sp || !buf || !buflen) return slab_fail(B2FFT_E_INVALID, "bad argument");
+    DevGuard guard(sp->device);
+    SLAB_CUDA(cudaDeviceSynchronize());
+    std::string out;
+    for (size_t i = 0; i < sp->marks.size(); ++i) {
+        float ms = 0;
+        if (i > 0) SLAB_CUDA(cudaEventElapsedTime(&ms, sp->marks[0].second, sp->marks[i].second));
+        char item[96];
+        snprintf(item, sizeof item, "%s:%.4f;", sp->marks[i].first.c_str(), ms);
+        out += item;
+    }
+    snprintf(buf, buflen, "%s", out.c_str());
     return B2FFT_OK;
 }
 
@@ -391,6 +439,7 @@ int b2fft_slab_plan_destroy(b2fft_slab_plan* sp) {
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {sp->ev_start, sp->ev_sx, sp->ev_sz})
         if (ev) cudaEventDestroy(ev);
+    sp->clear_marks();
     if (sp->d_flag_ptrs) cudaFree(sp->d_flag_ptrs);
     if (sp->d_err) cudaFree(sp->d_err);
     delete sp;

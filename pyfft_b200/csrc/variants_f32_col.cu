@@ -15,6 +15,7 @@ void register_f32_col(std::vector<KernelVariant>& out) {
 #define XT0 B2_VT0
 #define XC0 B2_VC0
 #define XU B2_VU
+#define XS B2_VS
 #include "variants.def"
 #undef X
 #undef XT
@@ -27,5 +28,6 @@ void register_f32_col(std::vector<KernelVariant>& out) {
 #undef XT0
 #undef XC0
 #undef XU
+#undef XS
 }
 }  // namespace b2

@@ -325,6 +325,18 @@ class SlabPlan(object):
         self._check(self._lib.b2fft_slab_plan_status(self._native, ctypes.byref(out)))
         return out.value
 
+    def set_trace(self, on=True):
+        if getattr(self, "_native", None) is not None:
+            self._check(self._lib.b2fft_slab_plan_set_trace(self._native, int(bool(on))))
+
+    def trace(self):
+        """[(phase, ms since the start of the last traced forward)] -- synchronises the device."""
+        if getattr(self, "_native", None) is None:
+            return []
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._check(self._lib.b2fft_slab_plan_trace(self._native, buf, len(buf)))
+        return [(k, float(v)) for k, v in (item.split(":") for item in buf.value.decode().split(";") if item)]
+
     def describe(self):
         if getattr(self, "_native", None) is None:
             return "exchange=%s" % self.exchange

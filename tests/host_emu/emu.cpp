@@ -566,6 +566,96 @@ static void check_fused2(const char* name) {
     if (!ok) ++g_fail;
 }
 
+// The shared-memory-resident fused two-step kernel (kernels.cuh fused2s_fft_kernel): step A threads store through
+// fused2s_store_a into the [k1][n2][W] intermediate (rows k1 < KS in "shared memory", the rest in the scratch slot), step B
+// threads read their column back with fused2s_load_b; parameters as VariantOpsFused2S::launch builds them.
+template <class CfgA, class CfgB, int KS, bool INV>
+static double run_fused2s(long long outer, long long inner, int grid, bool in_place, unsigned seed) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, N = N1 * N2;
+    const long long total = outer * N * inner;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T2> in_c(total), out_c(total), ref_in(total);
+    for (long long i = 0; i < total; ++i) { in_c[i].x = (T)nd(rng); in_c[i].y = (T)nd(rng); out_c[i].x = NAN; out_c[i].y = NAN; }
+    ref_in = in_c;
+    const long long slot_elems = (long long)(N1 - KS) * N2 * W;
+    std::vector<T2> scratch((size_t)grid * slot_elems + 1), smem_i((size_t)KS * N2 * W + 1);
+    auto t1 = make_fs_table<T>(N, N2, CfgA::TPC, 1), t2 = make_fs_table<T>(N, N2, CfgA::E, CfgA::TPC);
+    PassParams<T> p{};
+    p.in0 = reinterpret_cast<const T*>(in_c.data());
+    p.out0 = reinterpret_cast<T*>(in_place ? in_c.data() : out_c.data());
+    p.inner = inner; p.inner_blocks = inner / W; p.outer_stride = (long long)N * inner;
+    p.n_tiles = outer * p.inner_blocks;
+    p.out_inner = inner; p.out_outer_stride = p.outer_stride; p.out_blk_log2 = -1; p.in_blk_log2 = -1;
+    p.scale = (T)0.5; p.scale_mode = 1;
+    p.fs_t1 = reinterpret_cast<const T*>(t1.data()); p.fs_t2 = reinterpret_cast<const T*>(t2.data());
+    p.scratch = reinterpret_cast<T*>(scratch.data());
+    PassParams<T> pa = p, pb = p;
+    pa.inner = (long long)N2 * p.inner; pa.out0 = p.scratch; pa.scale_mode = 0; pa.fs_n2 = N2;
+    pb.in0 = p.scratch; pb.out_inner = (long long)N1 * p.out_inner; pb.fs_t1 = pb.fs_t2 = nullptr;
+    for (int bid = 0; bid < grid; ++bid) {
+        T2* slot = scratch.data() + (long long)bid * slot_elems;
+        for (long long sidx = bid; sidx < pa.n_tiles; sidx += grid) {
+            const long long o = sidx / pa.inner_blocks, ib = sidx - o * pa.inner_blocks;
+            for (auto& v : smem_i) { v.x = NAN; v.y = NAN; }
+            for (long long i = 0; i < slot_elems; ++i) { slot[i].x = NAN; slot[i].y = NAN; }
+            for (int c = 0; c < N2 / CfgA::G; ++c)
+                for (int tid = 0; tid < CfgA::THREADS; ++tid) {
+                    TileThread<CfgA, false, INV, true, true> th;
+                    fused2_setup_a<CfgA, CfgB>(th, tid, c, o * pa.outer_stride + ib * W, p.inner, 0);
+                    th.load(pa);
+                    th.template compute<0>(pa);
+                    th.apply_fs_twiddle(pa);
+                    fused2s_store_a<CfgA, CfgB, KS>(th, smem_i.data(), slot, 0ull);
+                }
+            for (int c = 0; c < N1 / CfgB::G; ++c)
+                for (int tid = 0; tid < CfgB::THREADS; ++tid) {
+                    TileThread<CfgB, false, INV, false, true> th;
+                    fused2_setup_b<CfgA, CfgB>(th, tid, c, o * pb.out_outer_stride + ib * W, p.out_inner, 0);
+                    fused2s_load_b<CfgA, CfgB, KS>(th, c * CfgB::G + th.g, smem_i.data(), slot, 0ull);
+                    th.template compute<0>(pb);
+                    th.store(pb);
+                }
+        }
+    }
+    const std::vector<T2>& got_c = in_place ? in_c : out_c;
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner; ++i) {
+            for (long long n = 0; n < N; ++n) {
+                const T2 v = ref_in[(o * N + n) * inner + i];
+                line[n] = INV ? cld(v.y, v.x) : cld(v.x, v.y);
+            }
+            ref_fft(line);
+            for (long long n = 0; n < N; ++n) {
+                cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+                want *= 0.5L;
+                const T2 g = got_c[(o * N + n) * inner + i];
+                double e = (double)std::abs(cld(g.x, g.y) - want);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(want);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <class CfgA, class CfgB, int KS>
+static void check_fused2s(const char* name) {
+    using T = typename CfgA::T;
+    const double tol = sizeof(T) == 4 ? 4e-6 : 2e-14;
+    double e0 = run_fused2s<CfgA, CfgB, KS, false>(1, 3 * CfgA::W, 2, false, 31);
+    double e1 = run_fused2s<CfgA, CfgB, KS, true>(2, CfgA::W, 1, true, 32);
+    bool ok = e0 < tol && e1 < tol;
+    std::printf("%-44s fused two-step (smem, ks=%d) N=%dx%d  err fwd(oop)=%.2e inv(in place)=%.2e thr=%d %s\n", name, KS, CfgA::N,
+                CfgB::N, e0, e1, CfgA::THREADS, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 #define CHKT(T, L, G, R0, R1, R2, R3) \
     check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
 

@@ -148,6 +148,11 @@ def main():
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                     ms = float(t.item())
                 N = float(n) ** 3
+                if hasattr(plan, "set_trace") and os.environ.get("SLAB_TRACE"):
+                    plan.set_trace(True)
+                    plan.forward()
+                    rec["trace_rank0"] = plan.trace()
+                    plan.set_trace(False)
                 rec["ms"] = ms
                 rec["gflops"] = 5.0 * N * math.log2(N) / (ms * 1e-3) / 1e9
                 rec["launches_per_step"] = (plan.launch_count - l0) / args.steps
