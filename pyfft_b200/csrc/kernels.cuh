@@ -4,11 +4,22 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "fft_core.cuh"
 
 namespace b2 {
+
+// resident-CTA counts (SMs x occupancy) are properties of a (kernel, device) pair
+#define B2_MAX_DEVICES 64
+inline int b2_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= B2_MAX_DEVICES) d = 0;
+    return d;
+}
 
 template <class Cfg, bool SPLIT, bool INV, int s, class TH>
 __device__ __forceinline__ void run_stages(TH& th, const PassParams<typename Cfg::T>& p,
@@ -777,7 +788,7 @@ template <class Cfg, int MINB, int NBUF>
 struct VariantOpsTma {
     using T = typename Cfg::T;
     using L = TmaRowLayout<Cfg, NBUF>;
-    static int& slots() { static int s = 0; return s; }   // resident CTAs on the device (SMs x occupancy)
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }   // resident CTAs (SMs x occupancy), per device   // resident CTAs on the device (SMs x occupancy)
     static cudaError_t prepare() {
         const int b = (int)L::TOTAL;
         cudaError_t e = cudaFuncSetAttribute(tile_fft_kernel_tma_row<Cfg, false, false, MINB, NBUF>,
@@ -849,11 +860,28 @@ inline b2_encode_tiled_fn b2_get_encode_tiled() {
 }
 
 // {inner (x elems_per_complex), N, outer} view of one plane pointer, boxes {W (x epc), NB, 1}
+// Encoded maps are cached per (pointer, geometry): a plan that is executed repeatedly on the same buffers -- the normal
+// case -- pays for cuTensorMapEncodeTiled once, not once per launch.
+struct B2MapKey {
+    const void* base; long long inner, outer; int epc, N, W, NB, esz, dev;
+    bool operator<(const B2MapKey& o) const {
+        return std::tie(base, inner, outer, epc, N, W, NB, esz, dev) < std::tie(o.base, o.inner, o.outer, o.epc, o.N, o.W, o.NB, o.esz, o.dev);
+    }
+};
+inline std::map<B2MapKey, CUtensorMap>& b2_map_cache() { static std::map<B2MapKey, CUtensorMap> m; return m; }
+inline std::mutex& b2_map_mutex() { static std::mutex m; return m; }
+
 template <typename T>
 inline cudaError_t b2_make_col_map(CUtensorMap* tm, const void* base, int epc, long long inner, int N, long long outer,
                                    int W, int NB) {
     b2_encode_tiled_fn enc = b2_get_encode_tiled();
     if (!enc) return cudaErrorNotSupported;
+    const B2MapKey key{base, inner, outer, epc, N, W, NB, (int)sizeof(T), b2_current_device()};
+    {
+        std::lock_guard<std::mutex> lk(b2_map_mutex());
+        auto it = b2_map_cache().find(key);
+        if (it != b2_map_cache().end()) { *tm = it->second; return cudaSuccess; }
+    }
     const cuuint64_t dims[3] = {(cuuint64_t)(inner * epc), (cuuint64_t)N, (cuuint64_t)outer};
     const cuuint64_t strides[2] = {(cuuint64_t)(inner * epc) * sizeof(T), (cuuint64_t)(inner * epc) * N * sizeof(T)};
     const cuuint32_t box[3] = {(cuuint32_t)(W * epc), (cuuint32_t)NB, 1};
@@ -861,14 +889,18 @@ inline cudaError_t b2_make_col_map(CUtensorMap* tm, const void* base, int epc, l
     CUresult r = enc(tm, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lk(b2_map_mutex());
+    if (b2_map_cache().size() >= 4096) b2_map_cache().clear();      // bounded: callers that stream through fresh buffers
+    b2_map_cache()[key] = *tm;
+    return cudaSuccess;
 }
 
 template <class Cfg, int MINB, int NBUF, bool FSCAP = false>
 struct VariantOpsTmaCol {
     using T = typename Cfg::T;
     using L = TmaRowLayout<Cfg, NBUF>;
-    static int& slots() { static int s = 0; return s; }
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }   // resident CTAs (SMs x occupancy), per device
     template <bool SPLIT, bool INV, bool BLK, bool FS = false>
     static cudaError_t attr() {
         return cudaFuncSetAttribute(tile_fft_kernel_tma_col<Cfg, SPLIT, INV, MINB, NBUF, BLK, FS>,
@@ -972,7 +1004,7 @@ template <class Cfg, int MINB>
 struct VariantOpsTmaColAlias {
     using T = typename Cfg::T;
     using L = TmaAliasLayout<Cfg>;
-    static int& slots() { static int s = 0; return s; }
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }   // resident CTAs (SMs x occupancy), per device
     template <bool SPLIT, bool INV, bool BLK>
     static cudaError_t attr() {
         return cudaFuncSetAttribute(tile_fft_kernel_tma_col_alias<Cfg, SPLIT, INV, MINB, BLK>,
@@ -1051,7 +1083,7 @@ template <class CfgA, class CfgB, int MINB>
 struct VariantOpsFused2 {
     using T = typename CfgA::T;
     static constexpr size_t SMEM = (size_t)(CfgA::SMEM_BYTES > CfgB::SMEM_BYTES ? CfgA::SMEM_BYTES : CfgB::SMEM_BYTES);
-    static int& slots() { static int s = 0; return s; }
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }   // resident CTAs (SMs x occupancy), per device
     static cudaError_t prepare() {
         cudaError_t e;
         if ((e = cudaFuncSetAttribute(fused2_fft_kernel<CfgA, CfgB, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1134,7 +1166,7 @@ struct VariantOpsFused2S {
     using T = typename CfgA::T;
     static constexpr size_t SMEM = (size_t)KS * CfgB::N * CfgA::W * 2 * sizeof(T);
     static_assert(SMEM <= 227 * 1024, "intermediate rows kept in shared memory must fit");
-    static int& slots() { static int s = 0; return s; }
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }   // resident CTAs (SMs x occupancy), per device
     static cudaError_t prepare() {
         cudaError_t e;
         if ((e = cudaFuncSetAttribute(fused2s_fft_kernel<CfgA, CfgB, KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -55,6 +55,25 @@ def test_invalid_arguments_are_value_errors(built_lib):
     assert built_lib.b2fft_execute(None, None, None, None, None, 0, 1, None) == _lib.E_INVALID
 
 
+def test_slab_plan_argument_validation(built_lib):
+    """b2fft_slab_*: bad decompositions are refused with E_INVALID before any device work."""
+    from pyfft_b200 import _lib
+    h = ctypes.c_void_p()
+
+    def create(dims, rank, nranks, prec=0):
+        return built_lib.b2fft_slab_plan_create(ctypes.byref(h), (ctypes.c_int64 * 3)(*dims), prec, 1, 1.0, 1, 0, rank, nranks, 8, 1, 3)
+    assert create((64, 64, 64), 0, 3) == _lib.E_INVALID and b"power of two" in built_lib.b2fft_slab_last_error()
+    assert create((64, 64, 64), 4, 4) == _lib.E_INVALID
+    assert create((64, 64, 48), 0, 4) == _lib.E_INVALID and b"powers of two" in built_lib.b2fft_slab_last_error()
+    assert create((2, 64, 64), 0, 4) == _lib.E_INVALID and b"divisible" in built_lib.b2fft_slab_last_error()
+    assert create((64, 64, 2), 0, 4) == _lib.E_INVALID
+    assert create((64, 64, 64), 0, 2, prec=5) == _lib.E_INVALID
+    assert built_lib.b2fft_slab_forward(None, None) == _lib.E_INVALID
+    assert built_lib.b2fft_slab_plan_destroy(None) == _lib.OK
+    # source-blocked loads are only defined for single-pass contiguous-axis plans
+    assert built_lib.b2fft_plan_set_input_blocks(None, 2, None) == _lib.E_INVALID
+
+
 def test_python_plan_validation_without_gpu():
     from pyfft_b200.cuda import Plan
     with pytest.raises(ValueError):

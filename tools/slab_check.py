@@ -49,19 +49,16 @@ def main():
                 continue
             yzx = ex.endswith("-yzx")
             chunks = int(ex.split("x")[1]) if ex.startswith("ncclx") else 1          # "ncclx8" = 8 pipelined chunks
-            xs = ex.startswith("xslab")               # "xslab" / "xslabx4" = 4 y-chunks / "xslabx8c1" = 1 exchange CTA per SM / "xslabx8z2" = 2 z-chunks
-            ctas = 3
-            zch = 1
-            if xs and "z" in ex[5:]:
-                ex, _, zz = ex.rpartition("z")
-                zch = int(zz)
-            if xs and "c" in ex[5:]:
-                ex_, _, cc = ex.rpartition("c")
-                ctas = int(cc)
-            else:
-                ex_ = ex
-            if xs and "x" in ex_[5:]:
-                chunks = int(ex_[5:].split("x")[1])
+            xs = ex.startswith("xslab")               # "xslab[xC][zK][cN]": C y-chunks, K z-chunks, N exchange CTAs per SM
+            ctas, zch = 3, 1
+            if xs:
+                import re
+                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?$", ex)
+                if not m:
+                    raise SystemExit("bad exchange spec " + ex)
+                chunks = int(m.group(1)) if m.group(1) else 8
+                zch = int(m.group(2)) if m.group(2) else 1
+                ctas = int(m.group(3)) if m.group(3) else 3
             plan = SlabPlan(shape, dtype=npdt, exchange="xslab" if xs else "nccl" if ex.startswith("nccl") else ex.split("-")[0],
                             yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas, z_chunks=zch)
             L = plan.L
@@ -74,7 +71,7 @@ def main():
                 for z0 in range(0, L["Zl"], zs):          # in pieces: no slab-sized temporaries
                     z1 = min(L["Zl"], z0 + zs)
                     plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, n, n, 2, dtype=fl, device=dev, generator=g)))
-            rec = {"n": n, "world": world, "exchange": ex + ("z%d" % zch if zch > 1 else ""), "dtype": args.dtype,
+            rec = {"n": n, "world": world, "exchange": ex, "dtype": args.dtype,
                    "y_chunks": plan.chunks, "z_chunks": getattr(plan, "z_chunks", 1)}
             fill()
             x_local = plan.slab.clone() if (args.check or n <= 1024) else None
