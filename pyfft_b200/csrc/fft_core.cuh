@@ -762,4 +762,120 @@ B2_HD void fused2s_load_b(TH& th, int k1, const vec2<typename CfgA::T>* smem_i, 
     }
 }
 
+// ------------------------------------------------------------------ lane-pair FFT (warp-shuffle exchange)
+// A length-N = 2E transform shared by two lanes of a warp (t = 0, 1): lane t holds x[2j + t] in v[j], does the E-point
+// FFT of its residue class in registers, lane 1 applies w_N^ka, and the final radix-2 stage pairs Z_0[ka] with Z_1[ka]:
+//     X[ka + E*kb] = Z_0[ka] + (-1)^kb Z_1[ka].
+// Each lane computes the pairs of half of the ka values; the halves it does not own go to the partner in ONE exchange of
+// E/2 complex values -- a warp shuffle on the device (shfl.sync.bfly, lane ^ 16), a plain swap in the host emulation --
+// instead of a shared-memory round trip.  Register r holds ka = brev(r), so after post():
+//     v[i]       = X[brev(i, L) + t]            i in [0, E/2)
+//     v[E/2 + i] = X[brev(i, L) + t + E]
+// i.e. the lane's outputs are a compile-time index plus t, which folds into its base pointers.
+template <typename T, int LOG2N, bool INV>
+struct PairFFT {
+    static constexpr int N = 1 << LOG2N, E = N / 2, L = LOG2N - 1, H = E / 2;
+    static_assert(LOG2N >= 2 && LOG2N <= 6, "the pair twiddles are 64th roots of unity");
+    using C = cpx<T>;
+    static constexpr int out_k(int i) { return brev(i, L); }       // + t (+ E for the upper half)
+    B2_HD static C sel(bool c, const C& a, const C& b) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (is_packed<T>::value) { C r; r.v = c ? a.v : b.v; return r; } else
+#endif
+        { return c ? a : b; }
+    }
+    B2_HD static void pre(C* v, int t, C* send) {
+        butterfly<E, 0, INV>(v);
+        static_for<1, E>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            constexpr int ka = brev(r, L);
+            v[r] = sel(t != 0, cmulc<ka * (64 / N), INV>(v[r]), v[r]);
+        });
+        static_for<0, H>([&](auto ic) { constexpr int i = decltype(ic)::value; send[i] = sel(t != 0, v[i], v[H + i]); });
+    }
+    B2_HD static void post(C* v, int t, const C* recv) {
+        const T sgn = t ? (T)-1 : (T)1;
+        static_for<0, H>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const C own = sel(t != 0, v[H + i], v[i]);
+            v[i] = cadd(own, recv[i]);
+            v[H + i] = cscale(csub(own, recv[i]), sgn);
+        });
+    }
+#if defined(__CUDA_ARCH__)
+    // the exchange itself: partner = lane ^ 16 (the two lanes of a pair sit in the two half-warps, one column each)
+    __device__ __forceinline__ static void exchange(const C* send, C* recv) {
+        static_for<0, H>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (is_packed<T>::value) {
+                recv[i].v = __shfl_xor_sync(0xffffffffu, send[i].v, 16);
+            } else {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, send[i].x, 16);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, send[i].y, 16);
+            }
+        });
+    }
+#endif
+};
+
+// ------------------------------------------------------------------ fused two-step strided program, lane-pair steps
+// The thread program of kernels.cuh fused2w_fft_kernel: N = N1*N2 as in fused2s (intermediate [k1][n2][W] in shared
+// memory, rows k1 >= KS in the global scratch slot), but every step is a PairFFT: a length-N1 (N2) transform is shared by
+// the two lanes (w, t = 0 / 1) of a warp that handle the same column, each holding N1/2 (N2/2) elements, with the radix-2
+// stage exchanged by warp shuffle.  Twice the threads per super-tile of the register-FFT version at half the registers.
+template <int LOG2A, int LOG2B, int W_, int KS, bool INV>
+struct Fused2W {
+    using T = float;
+    using C = cpx<T>;
+    using T2 = vec2<T>;
+    using PA = PairFFT<T, LOG2A, INV>;
+    using PB = PairFFT<T, LOG2B, INV>;
+    static constexpr int W = W_, N1 = PA::N, N2 = PB::N, EA = PA::E, EB = PB::E, HA = PA::H, HB = PB::H;
+    static_assert(KS % 2 == 0 && KS <= N1, "lane pairs (k1, k1 + 1) stay on one side of the shared/global split");
+
+    // step A input: x[n1][n2][w] with n1 = 2j + t; `col` points at (n1 = 0, this n2, this w), rows are `stride` apart
+    B2_HD static void a_load(C* v, const T2* col, long long stride, int t, unsigned long long pol) {
+        static_for<0, EA>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = ld_stream_c_pol(col + (long long)(2 * j + t) * stride, pol); });
+    }
+    // step A output k1 = out_k(i) + t (+ EA): times w_N^(k1*n2) (table [k1][N2]), into the intermediate
+    B2_HD static void a_store(const C* v, int t, long long n2, int w, const T2* fs_tab, T2* smem_i, T2* scratch_slot,
+                              unsigned long long pol) {
+        static_for<0, 2>([&](auto kbc) {
+            constexpr int kb = decltype(kbc)::value;
+            static_for<0, HA>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int k0 = PA::out_k(i) + EA * kb;                 // k1 = k0 + t
+                const C val = cmul<INV>(v[i + HA * kb], ld_c(fs_tab + (long long)(k0 + t) * N2 + n2));
+                if constexpr (k0 < KS) st_c(smem_i + ((long long)(k0 + t) * N2 + n2) * W + w, val);
+                else st_c_pol(scratch_slot + ((long long)(k0 + t - KS) * N2 + n2) * W + w, val, pol);
+            });
+        });
+    }
+    // step B input: intermediate row k1, n2 = 2j + t
+    B2_HD static void b_load(C* v, int t, int k1, int w, const T2* smem_i, const T2* scratch_slot, unsigned long long pol) {
+        if (k1 < KS) {
+            const T2* src = smem_i + ((long long)k1 * N2 + t) * W + w;
+            static_for<0, EB>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = ld_c(src + 2 * j * W); });
+        } else {
+            const T2* src = scratch_slot + ((long long)(k1 - KS) * N2 + t) * W + w;
+            static_for<0, EB>([&](auto jc) { constexpr int j = decltype(jc)::value; v[j] = ld_stream_c_pol(src + 2 * j * W, pol); });
+        }
+    }
+    // step B output k2 = out_k(i) + t (+ EB) -> row k1 + N1*k2 of the result; `col` points at (k = k1, this w), k2 rows are
+    // `stride` (= N1 * inner) apart; scale as TileThread::apply_scale (pyfft/kernel.py:23-37)
+    B2_HD static void b_store(const C* v, int t, T2* col, long long stride, T scale, int scale_mode, unsigned long long pol) {
+        static_for<0, 2>([&](auto kbc) {
+            constexpr int kb = decltype(kbc)::value;
+            static_for<0, HB>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int k0 = PB::out_k(i) + EB * kb;
+                C val = v[i + HB * kb];
+                if (scale_mode == 1) val = cscale(val, scale);
+                else if (scale_mode == 2) { T xr, xi; csplit(val, xr, xi); val = cmake<T>(xr / scale, xi / scale); }
+                st_c_pol(col + (long long)(k0 + t) * stride, val, pol);
+            });
+        });
+    }
+};
+
 }  // namespace b2

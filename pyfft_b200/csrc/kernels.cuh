@@ -681,6 +681,67 @@ fused2s_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
     }
 }
 
+
+// ------------------------------------------------------------------ fused two-step strided kernel, lane-pair steps + warp shuffles
+// fused2s is bound by issue latency: its register FFTs (32 and 64 elements per thread) leave room for only 8 warps per SM
+// (profiles/r02_fused2.md: 0.9 IPC, exact DRAM traffic).  Here every step is shared by a lane pair (16 and 32 elements per
+// thread, the radix-2 stage exchanged with shfl.sync -- see PairFFT), so a CTA has 512 threads at <= 128 registers: twice the
+// warps for the same shared-memory-resident intermediate, and room for a second register set that holds the next step-A
+// sub-tile while the current one is transformed.
+template <int LOG2A, int LOG2B, int KS, bool INV>
+__global__ void __launch_bounds__(512, 1)
+fused2w_fft_kernel(const __grid_constant__ PassParams<float> pa, const __grid_constant__ PassParams<float> pb,
+                   const long long inner_in, const long long inner_out) {
+    using F = Fused2W<LOG2A, LOG2B, 16, KS, INV>;
+    using T2 = vec2<float>;
+    using C = cpx<float>;
+    constexpr int W = F::W, N1 = F::N1, N2 = F::N2, G = 512 / (2 * W);
+    static_assert(N2 % G == 0 && N1 % G == 0, "sub-tiles must divide the super-tile");
+    constexpr int NSA = N2 / G, NSB = N1 / G;
+    extern __shared__ __align__(16) unsigned char b2_smem_raw[];
+    T2* smem_i = reinterpret_cast<T2*>(b2_smem_raw);
+    const int tid = (int)threadIdx.x;
+    const int w = tid % W, t = (tid / W) & 1, g = tid / (2 * W);
+    T2* scratch_slot = reinterpret_cast<T2*>(pa.out0) + (long long)blockIdx.x * ((long long)(N1 - KS) * N2 * W);
+    const T2* fs_tab = reinterpret_cast<const T2*>(pa.fs_t2);
+    unsigned long long pol_stream, pol_scratch;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_scratch));
+    for (long long s = blockIdx.x; s < pa.n_tiles; s += gridDim.x) {
+        const long long o = s / pa.inner_blocks, ib = s - o * pa.inner_blocks;
+        const T2* in_col = reinterpret_cast<const T2*>(pa.in0) + o * pa.outer_stride + ib * W + w;
+        {
+            C va[F::EA], vb[F::EA], send[F::HA], recv[F::HA];
+            F::a_load(va, in_col + (long long)g * inner_in, pa.inner, t, pol_stream);
+            static_for<0, NSA>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                C* cur = (c % 2 == 0) ? va : vb;
+                C* nxt = (c % 2 == 0) ? vb : va;
+                if constexpr (c + 1 < NSA) F::a_load(nxt, in_col + (long long)((c + 1) * G + g) * inner_in, pa.inner, t, pol_stream);
+                F::PA::pre(cur, t, send);
+                F::PA::exchange(send, recv);
+                F::PA::post(cur, t, recv);
+                F::a_store(cur, t, c * G + g, w, fs_tab, smem_i, scratch_slot, pol_scratch);
+            });
+        }
+        __syncthreads();                                         // the whole intermediate is in place
+        {
+            C v[F::EB], send[F::HB], recv[F::HB];
+            T2* out_col = reinterpret_cast<T2*>(pb.out0) + o * pb.out_outer_stride + ib * W + w;
+#pragma unroll 1
+            for (int c = 0; c < NSB; ++c) {
+                const int k1 = c * G + g;
+                F::b_load(v, t, k1, w, smem_i, scratch_slot, pol_scratch);
+                F::PB::pre(v, t, send);
+                F::PB::exchange(send, recv);
+                F::PB::post(v, t, recv);
+                F::b_store(v, t, out_col + (long long)k1 * inner_out, pb.out_inner, pb.scale, pb.scale_mode, pol_stream);
+            }
+        }
+        __syncthreads();                                         // intermediate fully read before the next super-tile overwrites it
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -1238,6 +1299,79 @@ struct VariantOpsFused2S {
     }
 };
 
+
+template <int LOG2A, int LOG2B, int KS>
+struct VariantOpsFused2W {
+    using T = float;
+    static constexpr int N1 = 1 << LOG2A, N2 = 1 << LOG2B, W = 16;
+    static constexpr size_t SMEM = (size_t)KS * N2 * W * 2 * sizeof(T);
+    static_assert(SMEM <= 227 * 1024, "intermediate rows kept in shared memory must fit");
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }
+    static cudaError_t prepare() {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(fused2w_fft_kernel<LOG2A, LOG2B, KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(fused2w_fft_kernel<LOG2A, LOG2B, KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM)) != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused2w_fft_kernel<LOG2A, LOG2B, KS, false>, 512, SMEM);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return cudaSuccess;
+    }
+    static int grid_slots() {
+        if (slots() <= 0 && prepare() != cudaSuccess) return -1;
+        return slots();
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        if (split || p.out_blk_log2 >= 0 || p.outer_div > 0 || !p.scratch || !p.fs_t2) return cudaErrorNotSupported;
+        if (p.n_tiles <= 0) return cudaSuccess;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        long long ctas = p.n_tiles;
+        if (ctas > slots()) ctas = slots();
+        if (ctas > p.scratch_slots) ctas = p.scratch_slots;
+        if (p.max_ctas > 0 && ctas > p.max_ctas) ctas = p.max_ctas;
+        if (ctas <= 0) return cudaErrorInvalidValue;
+        PassParams<T> pa = p, pb = p;
+        pa.inner = (long long)N2 * p.inner;               // n1 stride
+        pa.out0 = p.scratch;
+        pb.out_inner = (long long)N1 * p.out_inner;       // k2 stride in the output
+        const dim3 grid((unsigned)ctas), block(512);
+        if (inv) fused2w_fft_kernel<LOG2A, LOG2B, KS, true><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        else fused2w_fft_kernel<LOG2A, LOG2B, KS, false><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused2w_fft_kernel<LOG2A, LOG2B, KS, false>, 512, SMEM) != cudaSuccess) return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v{};
+        v.name = name;
+        v.prec = 0;
+        v.log2n = LOG2A + LOG2B;
+        v.log2n1 = LOG2A;
+        v.W = W; v.G = 512 / (2 * W); v.E = N1; v.S = 1;       // E = N1: the inter-step twiddle table is [k1][N2]
+        v.S_b = 1; v.E_b = N2;
+        for (int s = 0; s < 4; ++s) { v.radix[s] = s == 0 ? N1 : 1; v.radix_b[s] = s == 0 ? N2 : 1; }
+        v.threads = 512;
+        v.smem_bytes = (long long)SMEM;
+        v.minb = 1;
+        v.kind = 3;
+        v.slot_elems = (long long)(N1 - KS) * N2 * W;
+        if (v.slot_elems == 0) v.slot_elems = W;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        v.grid_slots = &grid_slots;
+        return v;
+    }
+};
+
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x
 #define B2_STR(x) B2_STR2(x)
@@ -1298,6 +1432,12 @@ struct VariantOpsFused2S {
     out.push_back(::b2::VariantOpsFused2S<::b2::TileCfg<T, L1, W, GA, (1 << L1)>,                     \
                                           ::b2::TileCfg<T, L2, W, GB, (1 << L2)>, KS>::make(          \
         #T "_n" B2_STR(L1) "+" B2_STR(L2) "_w" B2_STR(W) "_g" B2_STR(GA) "+" B2_STR(GB) "_ks" B2_STR(KS) "_fused2s"));
+
+// B2_VW(log2n1, log2n2, KS): fused two-step strided variant (complex64, W = 16, 512 threads) whose steps are lane-pair FFTs
+// with a warp-shuffle exchange; KS rows of the intermediate in shared memory
+#define B2_VW(L1, L2, KS)                                                                            \
+    out.push_back(::b2::VariantOpsFused2W<L1, L2, KS>::make(                                          \
+        "float_n" B2_STR(L1) "+" B2_STR(L2) "_w16_pair_ks" B2_STR(KS) "_fused2w"));
 
 void register_f32_row(std::vector<KernelVariant>& out);
 void register_f32_col(std::vector<KernelVariant>& out);

@@ -16,6 +16,7 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #define XC0 B2_VC0
 #define XU B2_VU
 #define XS B2_VS
+#define XW B2_VW
 #include "variants.def"
 #undef X
 #undef XT
@@ -29,5 +30,6 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #undef XC0
 #undef XU
 #undef XS
+#undef XW
 }
 }  // namespace b2

@@ -656,6 +656,95 @@ static void check_fused2s(const char* name) {
     if (!ok) ++g_fail;
 }
 
+// The lane-pair fused two-step kernel (kernels.cuh fused2w_fft_kernel): the same thread-level functions (Fused2W /
+// PairFFT), with the warp shuffle replaced by handing each lane its partner's `send` array.
+template <int LOG2A, int LOG2B, int KS, bool INV>
+static double run_fused2w(long long outer, long long inner, int grid, bool in_place, unsigned seed) {
+    using F = Fused2W<LOG2A, LOG2B, 16, KS, INV>;
+    using T = float;
+    using T2 = vec2<T>;
+    using C = cpx<T>;
+    constexpr int W = F::W, N1 = F::N1, N2 = F::N2, N = N1 * N2, G = 512 / (2 * W), THREADS = 512;
+    const long long total = outer * N * inner;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T2> in_c(total), out_c(total), ref_in(total);
+    for (long long i = 0; i < total; ++i) { in_c[i].x = (T)nd(rng); in_c[i].y = (T)nd(rng); out_c[i].x = NAN; out_c[i].y = NAN; }
+    ref_in = in_c;
+    const long long slot_elems = (long long)(N1 - KS) * N2 * W;
+    std::vector<T2> scratch((size_t)grid * slot_elems + 1), smem_i((size_t)KS * N2 * W + 1);
+    auto tab = make_fs_table<T>(N, N2, N1, 1);                       // [k1][N2]: w_N^(k1*n2), as api.cu fused_tables() requests it
+    const long long inner_blocks = inner / W, outer_stride = (long long)N * inner, n_super = outer * inner_blocks;
+    T2* out_base = in_place ? in_c.data() : out_c.data();
+    for (int bid = 0; bid < grid; ++bid) {
+        T2* slot = scratch.data() + (long long)bid * slot_elems;
+        for (long long sidx = bid; sidx < n_super; sidx += grid) {
+            const long long o = sidx / inner_blocks, ib = sidx - o * inner_blocks;
+            for (auto& v : smem_i) { v.x = NAN; v.y = NAN; }
+            for (long long i = 0; i < slot_elems; ++i) { slot[i].x = NAN; slot[i].y = NAN; }
+            for (int c = 0; c < N2 / G; ++c)
+                for (int pair = 0; pair < THREADS / 2; ++pair) {         // the two lanes (w, t = 0 / 1) of column (g, w)
+                    const int w = pair % W, g = pair / W;
+                    C v[2][F::EA], send[2][F::HA];
+                    for (int t = 0; t < 2; ++t) {
+                        F::a_load(v[t], in_c.data() + o * outer_stride + ib * W + w + (long long)(c * G + g) * inner, (long long)N2 * inner, t, 0ull);
+                        F::PA::pre(v[t], t, send[t]);
+                    }
+                    for (int t = 0; t < 2; ++t) {
+                        F::PA::post(v[t], t, send[1 - t]);
+                        F::a_store(v[t], t, c * G + g, w, tab.data(), smem_i.data(), slot, 0ull);
+                    }
+                }
+            std::vector<T2> result((size_t)N * W);
+            for (int c = 0; c < N1 / G; ++c)
+                for (int pair = 0; pair < THREADS / 2; ++pair) {
+                    const int w = pair % W, g = pair / W, k1 = c * G + g;
+                    C v[2][F::EB], send[2][F::HB];
+                    for (int t = 0; t < 2; ++t) {
+                        F::b_load(v[t], t, k1, w, smem_i.data(), slot, 0ull);
+                        F::PB::pre(v[t], t, send[t]);
+                    }
+                    for (int t = 0; t < 2; ++t) {
+                        F::PB::post(v[t], t, send[1 - t]);
+                        F::b_store(v[t], t, out_base + o * outer_stride + ib * W + w + (long long)k1 * inner, (long long)N1 * inner, (T)0.5, 1, 0ull);
+                    }
+                }
+        }
+    }
+    const std::vector<T2>& got_c = in_place ? in_c : out_c;
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner; ++i) {
+            for (long long n = 0; n < N; ++n) {
+                const T2 v = ref_in[(o * N + n) * inner + i];
+                line[n] = INV ? cld(v.y, v.x) : cld(v.x, v.y);
+            }
+            ref_fft(line);
+            for (long long n = 0; n < N; ++n) {
+                cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+                want *= 0.5L;
+                const T2 g = got_c[(o * N + n) * inner + i];
+                double e = (double)std::abs(cld(g.x, g.y) - want);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(want);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <int LOG2A, int LOG2B, int KS>
+static void check_fused2w(const char* name) {
+    double e0 = run_fused2w<LOG2A, LOG2B, KS, false>(1, 48, 2, false, 41);
+    double e1 = run_fused2w<LOG2A, LOG2B, KS, true>(2, 16, 1, true, 42);
+    bool ok = e0 < 4e-6 && e1 < 4e-6;
+    std::printf("%-44s fused two-step (lane pairs, ks=%d) N=%dx%d  err fwd(oop)=%.2e inv(in place)=%.2e %s\n", name, KS, 1 << LOG2A,
+                1 << LOG2B, e0, e1, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 #define CHKT(T, L, G, R0, R1, R2, R3) \
     check_staged<TileCfg<T, L, 1, G, R0, R1, R2, R3>>(#T " n" #L " g" #G " r" #R0 "x" #R1 "x" #R2 "x" #R3 " tma", 2 * (G) + 1);
 

@@ -76,6 +76,27 @@ def _xslab_blocked_store(L, xfft, peers, chunks):
                 peers[h][off:off + Xb] = row[h * Xb:(h + 1) * Xb]
 
 
+def _xslab_pull(L, xslabs, chunks):
+    """Emulates the inverse x-slab exchange pass (csrc/slab.cu b2fft_slab_inverse): per y-chunk the X pass walks the rows
+    {all local z} x {y in chunk} through the two-level outer index and LOADS piece h of every row from rank h's x-slab
+    (b2fft_plan_set_input_blocks + b2fft_plan_set_outer_split, same numbers as slab.cu passes); returns the z-slab rows."""
+    Zl, Y, X, Z, Xb, G = L["Zl"], L["Y"], L["X"], L["Z"], L["Xb"], L["G"]
+    Yc = Y // chunks
+    rank_off = L["xs_peer_offset"]                                  # rank * Zl * Xb
+    out = np.zeros(Zl * Y * X, dtype=np.complex128)
+    for c in range(chunks):
+        blk0 = c * Yc * Z * Xb + rank_off                            # base of every source block for this chunk
+        out0 = c * Yc * X
+        outer_div, in_lo, in_hi, out_lo, out_hi = Yc, Z * Xb, Xb, X, Y * X
+        for o in range(Yc * Zl):
+            hi, lo = divmod(o, outer_div)                            # (local z, y in chunk)
+            for h in range(G):
+                src = blk0 + hi * in_hi + lo * in_lo
+                dst = out0 + hi * out_hi + lo * out_lo + h * Xb
+                out[dst:dst + Xb] = xslabs[h][src:src + Xb]
+    return out.reshape(Zl, Y, X)
+
+
 def _worker(rank, world, port, shape, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -135,7 +156,15 @@ def _worker(rank, world, port, shape, q):
         got3 = np.fft.fft(minex.reshape(Y, Z, L["Xb"]), axis=1)          # Z pass on [Y][Z][Xb]
         ref3 = want[:, :, rank * L["Xb"]:(rank + 1) * L["Xb"]].transpose(1, 0, 2)
         err_xs = float(np.abs(got3 - ref3).max() / np.abs(ref3).max())
-        q.put((rank, err_nccl, err_p2p, err_inv, err_xs))
+        # fused inverse of the x-slab mode: inverse Z pass in place on every rank's x-slab, then this rank's X pass pulls
+        # the pieces of its rows from all x-slabs, then the local Y pass
+        zinv_x = np.fft.ifft(got3, axis=1)                                # [Y][Z][Xb], z back in the space domain
+        gathered = [None] * world
+        dist.all_gather_object(gathered, zinv_x.reshape(-1))
+        rows = _xslab_pull(L, gathered, chunks=2)                          # [Zl][Y][X], still transformed along y and x
+        back_x = np.fft.ifft(np.fft.ifft(rows, axis=2), axis=1)
+        err_pull = float(np.abs(back_x - slab).max())
+        q.put((rank, err_nccl, err_p2p, err_inv, max(err_xs, err_pull)))
     finally:
         dist.destroy_process_group()
 
