@@ -101,7 +101,9 @@ struct Registry {
         // pitch the single-pass TMA-staged tiles are faster (their neighbours share DRAM pages) and stay the default.
         static const int fused_mode = [] { const char* e = getenv("B2FFT_FUSED2"); return e ? atoi(e) : 1; }();   // 0 never, 1 large pitch, 2 always
         const long long pitch0 = inner * (prec ? 16 : 8);
-        if (!contiguous && fused_mode > 0 && (fused_mode > 1 || pitch0 >= (256 << 10)))
+        // complex64 N = 2048: the streamed fused kernel also beats the TMA-staged W = 4 tiles at small pitch (16 KiB: 4717 against
+        // 4367 GB/s, profiles/r02_fused2p.md), so it is taken whenever 16 columns divide the inner stride
+        if (!contiguous && fused_mode > 0 && (fused_mode > 1 || pitch0 >= (256 << 10) || (prec == 0 && log2n == 11)))
             for (size_t i = 0; i < n_default; ++i)
                 if (v[i].kind == 3 && ok(v[i])) return (int)i;
         const long long pitch = inner * (prec ? 16 : 8);

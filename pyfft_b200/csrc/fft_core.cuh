@@ -612,6 +612,29 @@ struct TileThread {
         });
     }
 
+    // ---- the same for one thread per column (TPC == 1), split so that the table loads can be issued ahead of the
+    //      butterflies: w_N^(k1*n2), k1 = 4a + b, is the product of w^(4a*n2) and w^(b*n2) -- E/4 + 2 table entries per
+    //      thread instead of E - 1 (one extra rounding on the products, as for the stage twiddles with TWP)
+    B2_HD void fs_base_load(const PassParams<T>& p, C (&lo)[4], C (&hi)[E / 4]) const {
+        static_assert(TPC == 1 && S == 1 && E >= 8, "one register FFT per thread");
+        const T2* t2p = reinterpret_cast<const T2*>(p.fs_t2) + fs_n2i;
+        static_for<1, 4>([&](auto bc) { lo[decltype(bc)::value] = ld_c(t2p + (long long)decltype(bc)::value * p.fs_n2); });
+        static_for<1, E / 4>([&](auto ac) { hi[decltype(ac)::value] = ld_c(t2p + (long long)(4 * decltype(ac)::value) * p.fs_n2); });
+    }
+    B2_HD void fs_base_apply(const C (&lo)[4], const C (&hi)[E / 4]) {
+        constexpr int LG = ilog2(E);
+        static_for<1, E>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;            // k1
+            constexpr int a = k / 4, b = k % 4;
+            constexpr int q = brev(k, LG);
+            C wv;
+            if constexpr (a == 0) wv = lo[b];
+            else if constexpr (b == 0) wv = hi[a];
+            else wv = cmul<false>(hi[a], lo[b]);
+            v[q] = cmul<INV>(v[q], wv);
+        });
+    }
+
     // ---- scale / normalise (last pass only; pyfft/kernel.py:23-37)
     B2_HD void apply_scale(const PassParams<T>& p) {
         if (p.scale_mode == 1) {
@@ -761,6 +784,32 @@ B2_HD void fused2s_load_b(TH& th, int k1, const vec2<typename CfgA::T>* smem_i, 
         static_for<0, N2>([&](auto jc) { th.v[decltype(jc)::value] = ld_stream_c_pol(src + decltype(jc)::value * W, pol); });
     }
 }
+
+// ---- in-place streamed variant (kernels.cuh fused2p_fft_kernel): the input rows n = n1*N2 + n2 with n1 < KS arrive in
+// shared memory as the dense tile [n1][n2][W] (asynchronous 16-byte copies issued while the previous super-tile is in its
+// step B), step A transforms column n2 IN PLACE (entry n1 is replaced by entry k1 of the same column, so [k1][n2][W] is
+// what step B finds), the rows n1 >= KS that do not fit come straight from global memory one sub-tile ahead (`extra`).
+template <class CfgA, class CfgB, int KS, class TH>
+B2_HD void fused2p_load_a(TH& th, const vec2<typename CfgA::T>* smem_i, const cpx<typename CfgA::T>* extra) {
+    static_assert(CfgA::S == 1 && CfgA::TPC == 1, "step A is one register FFT per thread");
+    constexpr int W = CfgA::W, N2 = CfgB::N;
+    const vec2<typename CfgA::T>* src = smem_i + th.fs_n2i * W + th.w;
+    static_for<0, CfgA::N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;                  // n1
+        if constexpr (j < KS) th.v[j] = ld_c(src + (long long)j * N2 * W);
+        else th.v[j] = extra[j - KS];
+    });
+}
+// Chunk `idx` (16 bytes) of the staged part of a super-tile: row n = idx / CPP of the tile (CPP chunks per 128-byte row
+// piece), returns the element offset inside the row piece; the source is row n of the tile in global memory, the
+// destination row n of the dense shared-memory tile.
+template <class CfgA>
+struct Fused2PChunk {
+    static constexpr int EPC = 16 / (2 * (int)sizeof(typename CfgA::T));     // complex elements per 16-byte chunk
+    static constexpr int CPP = CfgA::W / EPC;                                // chunks per row piece
+    static B2_HD long long row(long long idx) { return idx / CPP; }
+    static B2_HD int elem(long long idx) { return (int)(idx % CPP) * EPC; }
+};
 
 // ------------------------------------------------------------------ lane-pair FFT (warp-shuffle exchange)
 // A length-N = 2E transform shared by two lanes of a warp (t = 0, 1): lane t holds x[2j + t] in v[j], does the E-point

@@ -682,6 +682,147 @@ fused2s_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
 }
 
 
+// ------------------------------------------------------------------ fused two-step strided kernel, streamed in place through shared memory
+// fused2s keeps the [k1][n2][W] intermediate in shared memory but loads step A through registers and has no global load in
+// flight during step B: with one CTA of 8 warps per SM the DRAM read stream of an SM stops for half of every super-tile
+// (profiles/r02_fused2.md: 0.9 IPC, long-scoreboard bound).  Here the shared-memory tile is also the landing zone of the
+// NEXT super-tile: as soon as a step-B sub-tile has pulled its GB rows k1 into registers (and the CTA has passed a
+// barrier) those rows are refilled with input rows n1 = k1 of the CTA's next super-tile by asynchronous 16-byte copies
+// (cp.async.cg, SASS LDGSTS: eight lanes per 128-byte row piece, no registers held), which run beside the radix-64
+// butterflies and the global stores of the current one.  Step A then finds its input in shared memory and transforms every
+// column in place.  The N1-KS rows that do not fit (1/8 of a 2048-point tile) are prefetched into L2 during step B and read
+// one sub-tile ahead during step A, as in fused2s.  DRAM sees one read and one write per element; both streams stay busy.
+__device__ __forceinline__ void b2_cp_async16(void* dst_smem, const void* src, unsigned long long pol) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void b2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void b2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// rows [row0, row0 + nrows) of the super-tile at `tile_in` (row pitch inner_in elements) -> dense tile rows in shared memory
+template <class CfgA, int THREADS>
+__device__ __forceinline__ void fused2p_stage_rows(const vec2<typename CfgA::T>* tile_in, long long inner_in,
+                                                   vec2<typename CfgA::T>* smem_i, int tid, int row0, int nrows,
+                                                   unsigned long long pol) {
+    using CH = Fused2PChunk<CfgA>;
+    static_assert(THREADS % CH::CPP == 0, "a thread keeps its chunk column");
+    constexpr int RPI = THREADS / CH::CPP;                       // rows per iteration of the CTA
+    const int q = CH::elem(tid), r0 = row0 + (int)CH::row(tid);
+    const vec2<typename CfgA::T>* src = tile_in + (long long)r0 * inner_in + q;
+    vec2<typename CfgA::T>* dst = smem_i + (long long)r0 * CfgA::W + q;
+    const int iters = nrows / RPI;                               // nrows is a multiple of RPI (checked by the caller's static_assert)
+#pragma unroll 8
+    for (int it = 0; it < iters; ++it) {
+        b2_cp_async16(dst, src, pol);
+        src += (long long)RPI * inner_in;
+        dst += RPI * CfgA::W;
+    }
+}
+
+template <class CfgA, class CfgB, int KS, bool INV>
+__global__ void __launch_bounds__(CfgA::THREADS, 1)
+fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, const __grid_constant__ PassParams<typename CfgA::T> pb,
+                   const long long inner_in, const long long inner_out) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    using C = cpx<T>;
+    static_assert(CfgA::THREADS == CfgB::THREADS && CfgA::W == CfgB::W, "both steps run on the same CTA shape");
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, GA = CfgA::G, GB = CfgB::G, THREADS = CfgA::THREADS;
+    static_assert(N2 % GA == 0 && N1 % GB == 0 && KS <= N1, "sub-tiles must divide the super-tile");
+    constexpr int NSA = N2 / GA, NSB = N1 / GB, NX = N1 - KS;
+    constexpr int RPI = THREADS / Fused2PChunk<CfgA>::CPP;
+    static_assert((GB * N2) % RPI == 0 && ((KS % GB) * N2) % RPI == 0 && (KS * N2) % RPI == 0, "staged row ranges are whole CTA iterations");
+    extern __shared__ __align__(16) unsigned char b2_smem_raw[];
+    T2* smem_i = reinterpret_cast<T2*>(b2_smem_raw);
+    const int tid = (int)threadIdx.x;
+    T2* scratch_slot = reinterpret_cast<T2*>(pa.out0) + (long long)blockIdx.x * ((long long)(NX > 0 ? NX : 1) * N2 * W);
+    const T2* in = reinterpret_cast<const T2*>(pa.in0);
+    unsigned long long pol_stream, pol_scratch;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_scratch));
+    using THA = TileThread<CfgA, false, INV, true, true>;
+    auto tile_in_base = [&](long long s) {
+        const long long o = s / pa.inner_blocks, ib = s - o * pa.inner_blocks;
+        return o * pa.outer_stride + ib * W;
+    };
+    long long s = blockIdx.x;
+    if (s < pa.n_tiles) fused2p_stage_rows<CfgA, THREADS>(in + tile_in_base(s), inner_in, smem_i, tid, 0, KS * N2, pol_stream);
+    b2_cp_async_commit();
+    for (; s < pa.n_tiles; s += gridDim.x) {
+        const long long o = s / pa.inner_blocks, ib = s - o * pa.inner_blocks;
+        const long long in_base = o * pa.outer_stride + ib * W;
+        {
+            THA th;
+            C xa[NX > 0 ? NX : 1], xb[NX > 0 ? NX : 1];
+            th.pol_in = pol_stream;
+            // rows n1 >= KS of sub-tile c: (n1*N2 + c*GA + g) * inner_in, one sub-tile ahead of the butterflies
+            auto load_extra = [&](C* x, int c) {
+                if constexpr (NX > 0) {
+                    const T2* p = in + in_base + ((long long)KS * N2 + c * GA + tid / W) * inner_in + tid % W;
+                    static_for<0, NX>([&](auto ic) {
+                        x[decltype(ic)::value] = ld_stream_c_pol(p + (long long)decltype(ic)::value * N2 * inner_in, pol_stream);
+                    });
+                }
+            };
+            // inter-step twiddles of sub-tile c (fs_base_load), also one sub-tile ahead: the table reads are L1 hits, but with
+            // two warps per scheduler nothing hides even that latency behind the butterflies unless they are issued early
+            C la[4], ha[N1 / 4], lb[4], hb[N1 / 4];
+            th.fs_n2i = tid / W;
+            th.fs_base_load(pa, la, ha);
+            load_extra(xa, 0);
+            b2_cp_async_wait<0>();
+            __syncthreads();                                     // the staged rows of every thread have landed
+            static_for<0, NSA>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                C* cur = (c % 2 == 0) ? xa : xb;
+                C* nxt = (c % 2 == 0) ? xb : xa;
+                C(&lc)[4] = (c % 2 == 0) ? la : lb;
+                C(&hc)[N1 / 4] = (c % 2 == 0) ? ha : hb;
+                C(&ln)[4] = (c % 2 == 0) ? lb : la;
+                C(&hn)[N1 / 4] = (c % 2 == 0) ? hb : ha;
+                if constexpr (c + 1 < NSA) {
+                    load_extra(nxt, c + 1);
+                    th.fs_n2i = (c + 1) * GA + tid / W;
+                    th.fs_base_load(pa, ln, hn);
+                }
+                fused2_setup_a<CfgA, CfgB>(th, tid, c, in_base, inner_in, 0);
+                fused2p_load_a<CfgA, CfgB, KS>(th, smem_i, cur);
+                th.template compute<0>(pa);
+                th.fs_base_apply(lc, hc);
+                fused2s_store_a<CfgA, CfgB, KS>(th, smem_i, scratch_slot, pol_scratch);   // same column, same thread: in place
+            });
+        }
+        __syncthreads();                                         // the whole intermediate is in place
+        {
+            const long long s2 = s + gridDim.x;
+            const bool has_next = s2 < pa.n_tiles;
+            const T2* next_in = in + (has_next ? tile_in_base(s2) : 0);
+            if (NX > 0 && has_next)                              // the rows that are not staged -> L2
+                for (int r = tid; r < NX * N2; r += THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(next_in + (long long)(KS * N2 + r) * inner_in));
+            TileThread<CfgB, false, INV, false, true> th;
+            th.pol_out = pol_stream;
+            const long long out_base = o * pb.out_outer_stride + ib * W;
+#pragma unroll 1
+            for (int c = 0; c < NSB; ++c) {
+                fused2_setup_b<CfgA, CfgB>(th, tid, c, out_base, inner_out, 0);
+                fused2s_load_b<CfgA, CfgB, KS>(th, c * GB + th.g, smem_i, scratch_slot, pol_scratch);
+                __syncthreads();                                 // rows k1 in [c*GB, c*GB + GB) are in registers: refill them
+                if (has_next) {
+                    const int k_lo = c * GB, k_hi = (c + 1) * GB < KS ? (c + 1) * GB : KS;
+                    if (k_hi > k_lo) fused2p_stage_rows<CfgA, THREADS>(next_in, inner_in, smem_i, tid, k_lo * N2, (k_hi - k_lo) * N2, pol_stream);
+                }
+                b2_cp_async_commit();
+                th.template compute<0>(pb);
+                th.store(pb);
+            }
+        }
+    }
+    b2_cp_async_wait<0>();
+}
+
+
 // ------------------------------------------------------------------ fused two-step strided kernel, lane-pair steps + warp shuffles
 // fused2s is bound by issue latency: its register FFTs (32 and 64 elements per thread) leave room for only 8 warps per SM
 // (profiles/r02_fused2.md: 0.9 IPC, exact DRAM traffic).  Here every step is shared by a lane pair (16 and 32 elements per
@@ -1222,22 +1363,29 @@ struct VariantOpsFused2 {
 };
 
 
-template <class CfgA, class CfgB, int KS>
+// P: the streamed in-place kernel (fused2p_fft_kernel) instead of fused2s_fft_kernel; same parameters, same scratch slot
+template <class CfgA, class CfgB, int KS, bool P = false>
 struct VariantOpsFused2S {
     using T = typename CfgA::T;
+    using KernFn = void (*)(const PassParams<T>, const PassParams<T>, const long long, const long long);
+    template <bool INV>
+    static KernFn kern() {
+        if constexpr (P) return &fused2p_fft_kernel<CfgA, CfgB, KS, INV>;
+        else return &fused2s_fft_kernel<CfgA, CfgB, KS, INV>;
+    }
     static constexpr size_t SMEM = (size_t)KS * CfgB::N * CfgA::W * 2 * sizeof(T);
     static_assert(SMEM <= 227 * 1024, "intermediate rows kept in shared memory must fit");
     static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }   // resident CTAs (SMs x occupancy), per device
     static cudaError_t prepare() {
         cudaError_t e;
-        if ((e = cudaFuncSetAttribute(fused2s_fft_kernel<CfgA, CfgB, KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if ((e = cudaFuncSetAttribute(kern<false>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(fused2s_fft_kernel<CfgA, CfgB, KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if ((e = cudaFuncSetAttribute(kern<true>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM)) != cudaSuccess) return e;
         int dev = 0, sms = 0, occ = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused2s_fft_kernel<CfgA, CfgB, KS, false>, CfgA::THREADS, SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern<false>(), CfgA::THREADS, SMEM);
         if (e != cudaSuccess) return e;
         slots() = sms * (occ > 0 ? occ : 1);
         return cudaSuccess;
@@ -1265,13 +1413,13 @@ struct VariantOpsFused2S {
         pb.out_inner = (long long)CfgA::N * p.out_inner;  // k2 stride in the output
         pb.fs_t1 = pb.fs_t2 = nullptr;
         const dim3 grid((unsigned)ctas), block(CfgA::THREADS);
-        if (inv) fused2s_fft_kernel<CfgA, CfgB, KS, true><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
-        else fused2s_fft_kernel<CfgA, CfgB, KS, false><<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        if (inv) (*kern<true>())<<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
+        else (*kern<false>())<<<grid, block, SMEM, stream>>>(pa, pb, p.inner, p.out_inner);
         return cudaGetLastError();
     }
     static int occupancy() {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused2s_fft_kernel<CfgA, CfgB, KS, false>, CfgA::THREADS, SMEM) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern<false>(), CfgA::THREADS, SMEM) !=
             cudaSuccess)
             return -1;
         return n;
@@ -1432,6 +1580,12 @@ struct VariantOpsFused2W {
     out.push_back(::b2::VariantOpsFused2S<::b2::TileCfg<T, L1, W, GA, (1 << L1)>,                     \
                                           ::b2::TileCfg<T, L2, W, GB, (1 << L2)>, KS>::make(          \
         #T "_n" B2_STR(L1) "+" B2_STR(L2) "_w" B2_STR(W) "_g" B2_STR(GA) "+" B2_STR(GB) "_ks" B2_STR(KS) "_fused2s"));
+
+// B2_VP: like B2_VS with the streamed in-place kernel (asynchronous refill of the shared-memory tile during step B)
+#define B2_VP(T, L1, L2, W, GA, GB, KS)                                                              \
+    out.push_back(::b2::VariantOpsFused2S<::b2::TileCfg<T, L1, W, GA, (1 << L1)>,                     \
+                                          ::b2::TileCfg<T, L2, W, GB, (1 << L2)>, KS, true>::make(    \
+        #T "_n" B2_STR(L1) "+" B2_STR(L2) "_w" B2_STR(W) "_g" B2_STR(GA) "+" B2_STR(GB) "_ks" B2_STR(KS) "_fused2p"));
 
 // B2_VW(log2n1, log2n2, KS): fused two-step strided variant (complex64, W = 16, 512 threads) whose steps are lane-pair FFTs
 // with a warp-shuffle exchange; KS rows of the intermediate in shared memory

@@ -17,6 +17,7 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #define XU B2_VU
 #define XS B2_VS
 #define XW B2_VW
+#define XP B2_VP
 #include "variants.def"
 #undef X
 #undef XT
@@ -31,5 +32,6 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #undef XU
 #undef XS
 #undef XW
+#undef XP
 }
 }  // namespace b2

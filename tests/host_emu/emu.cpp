@@ -656,6 +656,129 @@ static void check_fused2s(const char* name) {
     if (!ok) ++g_fail;
 }
 
+// The streamed in-place fused two-step kernel (kernels.cuh fused2p_fft_kernel), in the kernel's own order of events: the
+// staged rows of a super-tile are copied chunk by chunk (Fused2PChunk, as fused2p_stage_rows does) into the shared-memory
+// tile; step A reads them back with fused2p_load_a (rows n1 >= KS from global memory), transforms in place; step B
+// sub-tile c first loads ALL its threads, then the rows it has freed are refilled with the CTA's next super-tile (what the
+// cp.async copies do after the barrier), then the threads compute and store -- so a refill that touched a row still to
+// be read, or a wrong chunk address, shows up as a wrong result of the current or the next super-tile.
+template <class CfgA, class CfgB, int KS, bool INV>
+static double run_fused2p(long long outer, long long inner, int grid, bool in_place, unsigned seed) {
+    using T = typename CfgA::T;
+    using T2 = vec2<T>;
+    using C = cpx<T>;
+    using CH = Fused2PChunk<CfgA>;
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, N = N1 * N2, NX = N1 - KS, THREADS = CfgA::THREADS;
+    const long long total = outer * N * inner;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T2> in_c(total), out_c(total), ref_in(total);
+    for (long long i = 0; i < total; ++i) { in_c[i].x = (T)nd(rng); in_c[i].y = (T)nd(rng); out_c[i].x = NAN; out_c[i].y = NAN; }
+    ref_in = in_c;
+    const long long slot_elems = (long long)(NX > 0 ? NX : 1) * N2 * W;
+    std::vector<T2> scratch((size_t)grid * slot_elems + 1);
+    auto t1 = make_fs_table<T>(N, N2, CfgA::TPC, 1), t2 = make_fs_table<T>(N, N2, CfgA::E, CfgA::TPC);
+    PassParams<T> p{};
+    p.in0 = reinterpret_cast<const T*>(in_c.data());
+    p.out0 = reinterpret_cast<T*>(in_place ? in_c.data() : out_c.data());
+    p.inner = inner; p.inner_blocks = inner / W; p.outer_stride = (long long)N * inner;
+    p.n_tiles = outer * p.inner_blocks;
+    p.out_inner = inner; p.out_outer_stride = p.outer_stride; p.out_blk_log2 = -1; p.in_blk_log2 = -1;
+    p.scale = (T)0.5; p.scale_mode = 1;
+    p.fs_t1 = reinterpret_cast<const T*>(t1.data()); p.fs_t2 = reinterpret_cast<const T*>(t2.data());
+    p.scratch = reinterpret_cast<T*>(scratch.data());
+    PassParams<T> pa = p, pb = p;
+    pa.inner = (long long)N2 * p.inner; pa.out0 = p.scratch; pa.scale_mode = 0; pa.fs_n2 = N2;
+    pb.in0 = p.scratch; pb.out_inner = (long long)N1 * p.out_inner; pb.fs_t1 = pb.fs_t2 = nullptr;
+    auto tile_base = [&](long long sidx) {
+        const long long o = sidx / pa.inner_blocks, ib = sidx - o * pa.inner_blocks;
+        return o * pa.outer_stride + ib * W;
+    };
+    // rows [row0, row0 + nrows) of the tile at `base`: every 16-byte chunk, one "thread" at a time
+    auto stage = [&](std::vector<T2>& smem, long long base, int row0, int nrows) {
+        for (long long idx = 0; idx < (long long)nrows * CH::CPP; ++idx) {
+            const long long r = row0 + CH::row(idx);
+            const int q = CH::elem(idx);
+            for (int e = 0; e < CH::EPC; ++e) smem[r * W + q + e] = in_c[base + r * inner + q + e];
+        }
+    };
+    for (int bid = 0; bid < grid; ++bid) {
+        T2* slot = scratch.data() + (long long)bid * slot_elems;
+        std::vector<T2> smem_i((size_t)KS * N2 * W + 1);
+        for (auto& v : smem_i) { v.x = NAN; v.y = NAN; }
+        if (bid < pa.n_tiles) stage(smem_i, tile_base(bid), 0, KS * N2);
+        for (long long sidx = bid; sidx < pa.n_tiles; sidx += grid) {
+            const long long in_base = tile_base(sidx);
+            const long long o = sidx / pa.inner_blocks, ib = sidx - o * pa.inner_blocks;
+            for (long long i = 0; i < slot_elems; ++i) { slot[i].x = NAN; slot[i].y = NAN; }
+            for (int c = 0; c < N2 / CfgA::G; ++c)
+                for (int tid = 0; tid < THREADS; ++tid) {
+                    TileThread<CfgA, false, INV, true, true> th;
+                    C extra[NX > 0 ? NX : 1];
+                    for (int i = 0; i < NX; ++i)
+                        extra[i] = ld_c(in_c.data() + in_base + ((long long)(KS + i) * N2 + c * CfgA::G + tid / W) * inner + tid % W);
+                    fused2_setup_a<CfgA, CfgB>(th, tid, c, in_base, p.inner, 0);
+                    C lo[4], hi[N1 / 4];
+                    th.fs_base_load(pa, lo, hi);
+                    fused2p_load_a<CfgA, CfgB, KS>(th, smem_i.data(), extra);
+                    th.template compute<0>(pa);
+                    th.fs_base_apply(lo, hi);
+                    fused2s_store_a<CfgA, CfgB, KS>(th, smem_i.data(), slot, 0ull);
+                }
+            const long long s2 = sidx + grid;
+            for (int c = 0; c < N1 / CfgB::G; ++c) {
+                std::vector<TileThread<CfgB, false, INV, false, true>> th(THREADS);
+                for (int tid = 0; tid < THREADS; ++tid) {
+                    fused2_setup_b<CfgA, CfgB>(th[tid], tid, c, o * pb.out_outer_stride + ib * W, p.out_inner, 0);
+                    fused2s_load_b<CfgA, CfgB, KS>(th[tid], c * CfgB::G + th[tid].g, smem_i.data(), slot, 0ull);
+                }
+                const int k_lo = c * CfgB::G, k_hi = std::min((c + 1) * CfgB::G, KS);
+                for (int k = k_lo; k < k_hi; ++k)                     // freed rows: poison, then refill if there is a next tile
+                    for (int e = 0; e < N2 * W; ++e) { smem_i[(size_t)k * N2 * W + e].x = NAN; smem_i[(size_t)k * N2 * W + e].y = NAN; }
+                if (s2 < pa.n_tiles && k_hi > k_lo) stage(smem_i, tile_base(s2), k_lo * N2, (k_hi - k_lo) * N2);
+                for (int tid = 0; tid < THREADS; ++tid) {
+                    th[tid].template compute<0>(pb);
+                    th[tid].store(pb);
+                }
+            }
+        }
+    }
+    const std::vector<T2>& got_c = in_place ? in_c : out_c;
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long o = 0; o < outer; ++o)
+        for (long long i = 0; i < inner; ++i) {
+            for (long long n = 0; n < N; ++n) {
+                const T2 v = ref_in[(o * N + n) * inner + i];
+                line[n] = INV ? cld(v.y, v.x) : cld(v.x, v.y);
+            }
+            ref_fft(line);
+            for (long long n = 0; n < N; ++n) {
+                cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+                want *= 0.5L;
+                const T2 g = got_c[(o * N + n) * inner + i];
+                double e = (double)std::abs(cld(g.x, g.y) - want);
+                if (!(e == e)) e = 1e30;
+                if (e > max_err) max_err = e;
+                double m = (double)std::abs(want);
+                if (m > max_mag) max_mag = m;
+            }
+        }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <class CfgA, class CfgB, int KS>
+static void check_fused2p(const char* name) {
+    using T = typename CfgA::T;
+    const double tol = sizeof(T) == 4 ? 4e-6 : 2e-14;
+    double e0 = run_fused2p<CfgA, CfgB, KS, false>(1, 5 * CfgA::W, 2, false, 51);     // 5 super-tiles over 2 CTAs: refills + tails
+    double e1 = run_fused2p<CfgA, CfgB, KS, true>(3, CfgA::W, 1, true, 52);           // one CTA, in place
+    bool ok = e0 < tol && e1 < tol;
+    std::printf("%-44s fused two-step (streamed, ks=%d) N=%dx%d  err fwd(oop)=%.2e inv(in place)=%.2e thr=%d %s\n", name, KS, CfgA::N,
+                CfgB::N, e0, e1, CfgA::THREADS, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 // The lane-pair fused two-step kernel (kernels.cuh fused2w_fft_kernel): the same thread-level functions (Fused2W /
 // PairFFT), with the warp shuffle replaced by handing each lane its partner's `send` array.
 template <int LOG2A, int LOG2B, int KS, bool INV>

@@ -65,11 +65,13 @@ def test_layout_and_pitch_aware_variant_choice(built_lib):
     assert "_tma" not in _preview(built_lib, 4096, layout=0)[0]["variant"]
     # strided axes: TMA tensor staging for N >= 1024 while rows are < 256 KiB apart ...
     assert "_tmac" in _preview(built_lib, 1024, 1024)[1]["variant"]
-    assert "_tmac" in _preview(built_lib, 2048, 2048, 2048)[1]["variant"]
-    # ... and the fused two-step kernel (128-byte pieces on both DRAM sides) beyond, in both precisions,
-    z = _preview(built_lib, 2048, 2048, 2048)[2]
-    assert "_fused2" in z["variant"] and "_w16_" in z["variant"]
-    assert "_fused2" in _preview(built_lib, 1024, 1024, 1024)[2]["variant"]
+    assert "_tmac" in _preview(built_lib, 2048, 2048, 2048, layout=1)[1]["variant"]
+    # ... and the fused two-step kernel (128-byte pieces on both DRAM sides) beyond, in both precisions; complex64 axes of
+    # length 2048 take its streamed form (fused2p) at every pitch, complex64 1024 beyond 256 KiB
+    y, z = _preview(built_lib, 2048, 2048, 2048)[1:3]
+    assert y["variant"].endswith("_fused2p") and z["variant"].endswith("_fused2p") and "_w16_" in z["variant"]
+    assert _preview(built_lib, 1024, 1024, 1024)[2]["variant"].endswith("_fused2p")
+    assert "_fused2" not in _preview(built_lib, 8, 2048, 2048)[1]["variant"]         # inner stride 8: no 16-column tile
     assert "_fused2" in _preview(built_lib, 256, 64, 1024, prec=1)[2]["variant"]
     # ... unless the layout is split or the inner stride is not a multiple of 128 bytes: widest plain tile
     z = _preview(built_lib, 2048, 2048, 2048, layout=1)[2]
