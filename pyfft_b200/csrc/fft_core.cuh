@@ -810,6 +810,20 @@ struct Fused2PChunk {
     static B2_HD long long row(long long idx) { return idx / CPP; }
     static B2_HD int elem(long long idx) { return (int)(idx % CPP) * EPC; }
 };
+// Rows of the shared-memory tile owned by one warp of a step-B sub-tile (thread tid reads row k1 = c*GB + tid/W, so warp v
+// owns the RPW = 32/W rows c*GB + v*RPW + i) and the order in which the warp refills them: segment sg = the GA values of
+// n2 of step-A sub-tile sg; piece p < RPW*GA of a segment is row k0 + p/GA, n2 = sg*GA + p%GA; a warp iteration
+// covers PPI = 32/CPP pieces.
+template <class CfgA, class CfgB>
+struct Fused2PRows {
+    static constexpr int RPW = 32 / CfgA::W;
+    static constexpr int NSEG = CfgB::N / CfgA::G;
+    static constexpr int PPI = 32 / Fused2PChunk<CfgA>::CPP;
+    static constexpr int ITERS = RPW * CfgA::G / PPI;
+    static_assert(32 % CfgA::W == 0 && (RPW * CfgA::G) % PPI == 0, "whole warp iterations per segment");
+    static B2_HD int k_of(int k0, int p) { return k0 + p / CfgA::G; }
+    static B2_HD int row(int k0, int sg, int p) { return k_of(k0, p) * CfgB::N + sg * CfgA::G + p % CfgA::G; }   // tile row n
+};
 
 // ------------------------------------------------------------------ lane-pair FFT (warp-shuffle exchange)
 // A length-N = 2E transform shared by two lanes of a warp (t = 0, 1): lane t holds x[2j + t] in v[j], does the E-point

@@ -700,24 +700,28 @@ __device__ __forceinline__ void b2_cp_async_commit() { asm volatile("cp.async.co
 template <int PENDING>
 __device__ __forceinline__ void b2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
-// rows [row0, row0 + nrows) of the super-tile at `tile_in` (row pitch inner_in elements) -> dense tile rows in shared memory
-template <class CfgA, int THREADS>
-__device__ __forceinline__ void fused2p_stage_rows(const vec2<typename CfgA::T>* tile_in, long long inner_in,
-                                                   vec2<typename CfgA::T>* smem_i, int tid, int row0, int nrows,
-                                                   unsigned long long pol) {
+// Refill of the rows one WARP owns in step-B sub-tile c (the rows its own lanes have just read into registers: k1 =
+// c*GB + warp*RPW + i, so no CTA barrier is needed, only warp convergence): input rows n = k1*N2 + n2 of the super-tile
+// at `tile_in`, copied segment by segment (segment = the GA values of n2 of one step-A sub-tile) with one commit group per
+// segment, so that step A of the next super-tile can start on segment 0 while the later ones are still in flight.
+template <class CfgA, class CfgB, int KS>
+__device__ __forceinline__ void fused2p_refill(const vec2<typename CfgA::T>* tile_in, long long inner_in,
+                                               vec2<typename CfgA::T>* smem_i, int lane, int k0, bool on,
+                                               unsigned long long pol) {
     using CH = Fused2PChunk<CfgA>;
-    static_assert(THREADS % CH::CPP == 0, "a thread keeps its chunk column");
-    constexpr int RPI = THREADS / CH::CPP;                       // rows per iteration of the CTA
-    const int q = CH::elem(tid), r0 = row0 + (int)CH::row(tid);
-    const vec2<typename CfgA::T>* src = tile_in + (long long)r0 * inner_in + q;
-    vec2<typename CfgA::T>* dst = smem_i + (long long)r0 * CfgA::W + q;
-    const int iters = nrows / RPI;                               // nrows is a multiple of RPI (checked by the caller's static_assert)
-#pragma unroll 8
-    for (int it = 0; it < iters; ++it) {
-        b2_cp_async16(dst, src, pol);
-        src += (long long)RPI * inner_in;
-        dst += RPI * CfgA::W;
-    }
+    using M = Fused2PRows<CfgA, CfgB>;
+    const int q = CH::elem(lane), pl = (int)CH::row(lane);      // chunk column, piece within one warp iteration
+    static_for<0, M::NSEG>([&](auto sc) {
+        constexpr int sg = decltype(sc)::value;
+        if (on) {
+            static_for<0, M::ITERS>([&](auto ic) {
+                constexpr int it = decltype(ic)::value;
+                const int n = M::row(k0, sg, it * M::PPI + pl);
+                if (M::k_of(k0, it * M::PPI + pl) < KS) b2_cp_async16(smem_i + (long long)n * CfgA::W + q, tile_in + (long long)n * inner_in + q, pol);
+            });
+        }
+        b2_cp_async_commit();
+    });
 }
 
 template <class CfgA, class CfgB, int KS, bool INV>
@@ -727,15 +731,15 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
     using T = typename CfgA::T;
     using T2 = vec2<T>;
     using C = cpx<T>;
+    using M = Fused2PRows<CfgA, CfgB>;
     static_assert(CfgA::THREADS == CfgB::THREADS && CfgA::W == CfgB::W, "both steps run on the same CTA shape");
     constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, GA = CfgA::G, GB = CfgB::G, THREADS = CfgA::THREADS;
     static_assert(N2 % GA == 0 && N1 % GB == 0 && KS <= N1, "sub-tiles must divide the super-tile");
     constexpr int NSA = N2 / GA, NSB = N1 / GB, NX = N1 - KS;
-    constexpr int RPI = THREADS / Fused2PChunk<CfgA>::CPP;
-    static_assert((GB * N2) % RPI == 0 && ((KS % GB) * N2) % RPI == 0 && (KS * N2) % RPI == 0, "staged row ranges are whole CTA iterations");
+    static_assert(GB * W == THREADS && M::RPW * (THREADS / 32) == GB, "a step-B sub-tile is RPW rows per warp");
     extern __shared__ __align__(16) unsigned char b2_smem_raw[];
     T2* smem_i = reinterpret_cast<T2*>(b2_smem_raw);
-    const int tid = (int)threadIdx.x;
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     T2* scratch_slot = reinterpret_cast<T2*>(pa.out0) + (long long)blockIdx.x * ((long long)(NX > 0 ? NX : 1) * N2 * W);
     const T2* in = reinterpret_cast<const T2*>(pa.in0);
     unsigned long long pol_stream, pol_scratch;
@@ -747,8 +751,11 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
         return o * pa.outer_stride + ib * W;
     };
     long long s = blockIdx.x;
-    if (s < pa.n_tiles) fused2p_stage_rows<CfgA, THREADS>(in + tile_in_base(s), inner_in, smem_i, tid, 0, KS * N2, pol_stream);
-    b2_cp_async_commit();
+    {   // first super-tile of this CTA: the same NSB x NSEG commit groups a step B would have issued
+        const T2* first_in = in + (s < pa.n_tiles ? tile_in_base(s) : 0);
+        for (int c = 0; c < NSB; ++c)
+            fused2p_refill<CfgA, CfgB, KS>(first_in, inner_in, smem_i, lane, c * GB + warp * M::RPW, s < pa.n_tiles, pol_stream);
+    }
     for (; s < pa.n_tiles; s += gridDim.x) {
         const long long o = s / pa.inner_blocks, ib = s - o * pa.inner_blocks;
         const long long in_base = o * pa.outer_stride + ib * W;
@@ -771,8 +778,6 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
             th.fs_n2i = tid / W;
             th.fs_base_load(pa, la, ha);
             load_extra(xa, 0);
-            b2_cp_async_wait<0>();
-            __syncthreads();                                     // the staged rows of every thread have landed
             static_for<0, NSA>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 C* cur = (c % 2 == 0) ? xa : xb;
@@ -786,6 +791,10 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
                     th.fs_n2i = (c + 1) * GA + tid / W;
                     th.fs_base_load(pa, ln, hn);
                 }
+                // segment c of every row has landed once this thread's groups up to (last step-B sub-tile, c) are complete
+                // and every other thread has seen the same for its own
+                b2_cp_async_wait<NSA - 1 - c>();
+                __syncthreads();
                 fused2_setup_a<CfgA, CfgB>(th, tid, c, in_base, inner_in, 0);
                 fused2p_load_a<CfgA, CfgB, KS>(th, smem_i, cur);
                 th.template compute<0>(pa);
@@ -808,12 +817,8 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
             for (int c = 0; c < NSB; ++c) {
                 fused2_setup_b<CfgA, CfgB>(th, tid, c, out_base, inner_out, 0);
                 fused2s_load_b<CfgA, CfgB, KS>(th, c * GB + th.g, smem_i, scratch_slot, pol_scratch);
-                __syncthreads();                                 // rows k1 in [c*GB, c*GB + GB) are in registers: refill them
-                if (has_next) {
-                    const int k_lo = c * GB, k_hi = (c + 1) * GB < KS ? (c + 1) * GB : KS;
-                    if (k_hi > k_lo) fused2p_stage_rows<CfgA, THREADS>(next_in, inner_in, smem_i, tid, k_lo * N2, (k_hi - k_lo) * N2, pol_stream);
-                }
-                b2_cp_async_commit();
+                __syncwarp();                                    // this warp's rows are in registers: refill them
+                fused2p_refill<CfgA, CfgB, KS>(next_in, inner_in, smem_i, lane, c * GB + warp * M::RPW, has_next, pol_stream);
                 th.template compute<0>(pb);
                 th.store(pb);
             }

@@ -656,19 +656,21 @@ static void check_fused2s(const char* name) {
     if (!ok) ++g_fail;
 }
 
-// The streamed in-place fused two-step kernel (kernels.cuh fused2p_fft_kernel), in the kernel's own order of events: the
-// staged rows of a super-tile are copied chunk by chunk (Fused2PChunk, as fused2p_stage_rows does) into the shared-memory
-// tile; step A reads them back with fused2p_load_a (rows n1 >= KS from global memory), transforms in place; step B
-// sub-tile c first loads ALL its threads, then the rows it has freed are refilled with the CTA's next super-tile (what the
-// cp.async copies do after the barrier), then the threads compute and store -- so a refill that touched a row still to
-// be read, or a wrong chunk address, shows up as a wrong result of the current or the next super-tile.
+// The streamed in-place fused two-step kernel (kernels.cuh fused2p_fft_kernel), in the kernel's own order of events: a
+// warp refills the rows it owns (Fused2PRows / Fused2PChunk, as fused2p_refill does, lane by lane and segment by segment)
+// in the shared-memory tile; step A reads them back with fused2p_load_a (rows n1 >= KS from global memory), transforms in
+// place; in step B sub-tile c every WARP first loads all its lanes, then the rows it has freed are poisoned and refilled
+// with the CTA's next super-tile (what its cp.async copies do), then its lanes compute and store -- so a refill that
+// touched a row another warp still has to read, or a wrong chunk address, shows up as a wrong result of the current or the
+// next super-tile.
 template <class CfgA, class CfgB, int KS, bool INV>
 static double run_fused2p(long long outer, long long inner, int grid, bool in_place, unsigned seed) {
     using T = typename CfgA::T;
     using T2 = vec2<T>;
     using C = cpx<T>;
     using CH = Fused2PChunk<CfgA>;
-    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, N = N1 * N2, NX = N1 - KS, THREADS = CfgA::THREADS;
+    using M = Fused2PRows<CfgA, CfgB>;
+    constexpr int W = CfgA::W, N1 = CfgA::N, N2 = CfgB::N, N = N1 * N2, NX = N1 - KS, THREADS = CfgA::THREADS, GB = CfgB::G;
     const long long total = outer * N * inner;
     std::mt19937_64 rng(seed);
     std::normal_distribution<double> nd(0.0, 1.0);
@@ -694,19 +696,25 @@ static double run_fused2p(long long outer, long long inner, int grid, bool in_pl
         const long long o = sidx / pa.inner_blocks, ib = sidx - o * pa.inner_blocks;
         return o * pa.outer_stride + ib * W;
     };
-    // rows [row0, row0 + nrows) of the tile at `base`: every 16-byte chunk, one "thread" at a time
-    auto stage = [&](std::vector<T2>& smem, long long base, int row0, int nrows) {
-        for (long long idx = 0; idx < (long long)nrows * CH::CPP; ++idx) {
-            const long long r = row0 + CH::row(idx);
-            const int q = CH::elem(idx);
-            for (int e = 0; e < CH::EPC; ++e) smem[r * W + q + e] = in_c[base + r * inner + q + e];
+    // one warp's refill of the rows k0 .. k0 + RPW - 1 from the tile at `base` (fused2p_refill, all lanes and segments)
+    auto refill = [&](std::vector<T2>& smem, long long base, int k0) {
+        for (int lane = 0; lane < 32; ++lane) {
+            const int q = CH::elem(lane), pl = (int)CH::row(lane);
+            for (int sg = 0; sg < M::NSEG; ++sg)
+                for (int it = 0; it < M::ITERS; ++it) {
+                    if (M::k_of(k0, it * M::PPI + pl) >= KS) continue;
+                    const long long n = M::row(k0, sg, it * M::PPI + pl);
+                    for (int e = 0; e < CH::EPC; ++e) smem[n * W + q + e] = in_c[base + n * inner + q + e];
+                }
         }
     };
     for (int bid = 0; bid < grid; ++bid) {
         T2* slot = scratch.data() + (long long)bid * slot_elems;
         std::vector<T2> smem_i((size_t)KS * N2 * W + 1);
         for (auto& v : smem_i) { v.x = NAN; v.y = NAN; }
-        if (bid < pa.n_tiles) stage(smem_i, tile_base(bid), 0, KS * N2);
+        if (bid < pa.n_tiles)
+            for (int c = 0; c < N1 / GB; ++c)
+                for (int warp = 0; warp < THREADS / 32; ++warp) refill(smem_i, tile_base(bid), c * GB + warp * M::RPW);
         for (long long sidx = bid; sidx < pa.n_tiles; sidx += grid) {
             const long long in_base = tile_base(sidx);
             const long long o = sidx / pa.inner_blocks, ib = sidx - o * pa.inner_blocks;
@@ -726,21 +734,23 @@ static double run_fused2p(long long outer, long long inner, int grid, bool in_pl
                     fused2s_store_a<CfgA, CfgB, KS>(th, smem_i.data(), slot, 0ull);
                 }
             const long long s2 = sidx + grid;
-            for (int c = 0; c < N1 / CfgB::G; ++c) {
-                std::vector<TileThread<CfgB, false, INV, false, true>> th(THREADS);
-                for (int tid = 0; tid < THREADS; ++tid) {
-                    fused2_setup_b<CfgA, CfgB>(th[tid], tid, c, o * pb.out_outer_stride + ib * W, p.out_inner, 0);
-                    fused2s_load_b<CfgA, CfgB, KS>(th[tid], c * CfgB::G + th[tid].g, smem_i.data(), slot, 0ull);
+            for (int c = 0; c < N1 / GB; ++c)
+                for (int warp = 0; warp < THREADS / 32; ++warp) {
+                    std::vector<TileThread<CfgB, false, INV, false, true>> th(32);
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = warp * 32 + lane;
+                        fused2_setup_b<CfgA, CfgB>(th[lane], tid, c, o * pb.out_outer_stride + ib * W, p.out_inner, 0);
+                        fused2s_load_b<CfgA, CfgB, KS>(th[lane], c * GB + th[lane].g, smem_i.data(), slot, 0ull);
+                    }
+                    const int k0 = c * GB + warp * M::RPW;
+                    for (int k = k0; k < k0 + M::RPW && k < KS; ++k)      // freed rows: poison, then refill if there is a next tile
+                        for (int e = 0; e < N2 * W; ++e) { smem_i[(size_t)k * N2 * W + e].x = NAN; smem_i[(size_t)k * N2 * W + e].y = NAN; }
+                    if (s2 < pa.n_tiles) refill(smem_i, tile_base(s2), k0);
+                    for (int lane = 0; lane < 32; ++lane) {
+                        th[lane].template compute<0>(pb);
+                        th[lane].store(pb);
+                    }
                 }
-                const int k_lo = c * CfgB::G, k_hi = std::min((c + 1) * CfgB::G, KS);
-                for (int k = k_lo; k < k_hi; ++k)                     // freed rows: poison, then refill if there is a next tile
-                    for (int e = 0; e < N2 * W; ++e) { smem_i[(size_t)k * N2 * W + e].x = NAN; smem_i[(size_t)k * N2 * W + e].y = NAN; }
-                if (s2 < pa.n_tiles && k_hi > k_lo) stage(smem_i, tile_base(s2), k_lo * N2, (k_hi - k_lo) * N2);
-                for (int tid = 0; tid < THREADS; ++tid) {
-                    th[tid].template compute<0>(pb);
-                    th[tid].store(pb);
-                }
-            }
         }
     }
     const std::vector<T2>& got_c = in_place ? in_c : out_c;

@@ -11,7 +11,7 @@ echo "== axis 1024 (fused2p always)"; B2FFT_PREFER=$P2 B2FFT_FUSED2=2 timeout 30
 B2FFT_PREFER=$P2 B2FFT_FUSED2=2 timeout 300 python tools/axis_time.py --dims 256,1024,1024 --steps 5 --axes 2 2>&1 | cut -c1-200 | tee -a $OUT/axis_1024.txt
 B2FFT_PREFER=$P2 B2FFT_FUSED2=2 timeout 300 python tools/axis_time.py --dims 256,2048,2048 --steps 5 --axes 2 2>&1 | cut -c1-200 | tee -a $OUT/axis_slabY.txt
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,launch__registers_per_thread,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active
-B2FFT_PREFER=$P2 timeout 300 ncu --metrics $M --clock-control none -k regex:fused2p -s 1 -c 1 --csv --log-file $OUT/ncu_z.csv python tools/axis_time.py --dims 2048,64,2048 --axes 4 --steps 2 > $OUT/ncu_z.log 2>&1
+timeout 300 ncu --metrics $M --clock-control none -k regex:fused2p -s 1 -c 1 --csv --log-file $OUT/ncu_z.csv python tools/axis_time.py --dims 2048,64,2048 --axes 4 --steps 2 > $OUT/ncu_z.log 2>&1
 python - <<PY
 import csv
 rows = [r for r in csv.reader(open("$OUT/ncu_z.csv")) if len(r) > 10]
