@@ -131,6 +131,15 @@ B2FFT_API int b2fft_plan_set_outer_split(b2fft_plan* plan, int64_t outer_div, in
  * to a sliver of each SM lets the HBM-bound pass of the previous chunk run beside it.  0 = no cap. */
 B2FFT_API int b2fft_plan_set_exchange_ctas(b2fft_plan* plan, int ctas_per_sm);
 
+/* Slab pipeline.  A plan that consists of ONE strided-axis pass run by a kernel that supports it (the streamed fused
+ * two-step kernel, complex64 N = 2048 / 1024) publishes its progress: `counters` (device memory, 32-bit words, zeroed by
+ * the caller before every execute) gets one word per chunk of `outer_per_chunk` consecutive outer blocks ([n][inner]
+ * planes of the array); every finished tile adds 1 to its chunk's word with release semantics, so word k has reached
+ * *target (= outer_per_chunk * inner / W, W the kernel's tile width) when chunk k is complete.  A consumer on another stream can then work on chunk k while
+ * the launch continues behind it.  max_ctas > 0 caps the (persistent) grid, which leaves the remaining SMs to that
+ * consumer.  B2FFT_E_UNSUPPORTED if the plan's kernel cannot do it; counters = NULL switches it off. */
+B2FFT_API int b2fft_plan_set_progress(b2fft_plan* plan, void* counters, int64_t outer_per_chunk, int max_ctas, int64_t* target);
+
 /* Peer-visible device memory for the slab exchange: plain cudaMalloc'ed buffers whose CUDA IPC
  * handles (64 bytes) can be exchanged between the per-GPU processes (e.g. through
  * torch.distributed.all_gather_object) and opened on the other ranks. */
@@ -154,7 +163,8 @@ B2FFT_API int b2fft_plan_destroy(b2fft_plan* plan);
  * traffic on plan-owned streams -- see pyfft_b200/csrc/slab.cu.  Scaling follows pyfft/kernel.py:23-37 with
  * size = X*Y*Z.  Interleaved layout only.
  *
- *   y_chunks / z_chunks      pipeline depth of the exchange (0 = defaults 8 / 1)
+ *   y_chunks / z_chunks      pipeline depth of the exchange (0 = defaults: 8 y-chunks; 8 z-chunks when the Y pass can
+ *                            be hidden under the exchange -- see b2fft_slab_plan_set_overlap -- else 1)
  *   exchange_ctas_per_sm     grid cap of the NVLink-bound X pass (0 = none), see b2fft_plan_set_exchange_ctas
  * The caller provides the buffers (b2fft_slab_plan_sizes; e.g. b2fft_mem_alloc + b2fft_ipc_export/import between
  * processes, or plain cudaMalloc + cudaDeviceEnablePeerAccess inside one process) and passes, for EVERY rank r, the
@@ -169,6 +179,14 @@ B2FFT_API int b2fft_slab_plan_sizes(const b2fft_slab_plan* plan, size_t* slab_by
 /* {Z/G, X/G, y_chunks, z_chunks, Y/y_chunks, (Z/G)/z_chunks, G, rank} */
 B2FFT_API int b2fft_slab_plan_geometry(const b2fft_slab_plan* plan, int64_t out[8]);
 B2FFT_API int b2fft_slab_plan_attach(b2fft_slab_plan* plan, void* slab, void* const* xslab_of_rank, void* const* flags_of_rank);
+/* Hides the local Y pass under the exchange (forward transform, z_chunks > 1): the Y pass becomes ONE persistent launch
+ * over the whole slab that leaves `reserved_sms` SMs free and publishes a progress counter per z-chunk
+ * (b2fft_plan_set_progress); the X passes of z-chunk k -- whose stores are the exchange -- start on the free SMs as soon
+ * as chunk k is through its Y pass, instead of sharing every SM with the Y kernels.  reserved_sms = 0 switches it off
+ * (one Y launch per z-chunk, ordered by events), -1 picks the default (on for >= 4 ranks when the Y kernel supports
+ * progress counters, B2FFT_SLAB_OVERLAP_SMS overrides).  Returns B2FFT_E_UNSUPPORTED (and stays off) when the Y pass of
+ * these dimensions cannot publish progress.  Call before the first forward. */
+B2FFT_API int b2fft_slab_plan_set_overlap(b2fft_slab_plan* plan, int reserved_sms);
 B2FFT_API int b2fft_slab_forward(b2fft_slab_plan* plan, void* cuda_stream);
 B2FFT_API int b2fft_slab_inverse(b2fft_slab_plan* plan, void* cuda_stream);
 /* 0 = healthy; non-zero = a cross-rank wait timed out (a peer never signalled); synchronises the device */

@@ -307,6 +307,10 @@ struct b2fft_plan {
     const void* in_blk[B2_MAX_BLOCKS] = {};
     // two-level outer index of the last pass (b2fft_plan_set_outer_split)
     int exchange_max_ctas = 0;   // grid cap of the last pass (b2fft_plan_set_exchange_ctas)
+    // per-chunk progress counters of a single-pass plan (b2fft_plan_set_progress) and the grid cap that goes with them
+    unsigned* progress = nullptr;
+    long long progress_outer = 0;
+    int progress_max_ctas = 0;
     long long split_div = 0, split_in_lo = 0, split_in_hi = 0, split_out_lo = 0, split_out_hi = 0;
     std::atomic<long long> launches{0};
     long long fused_slots_for(long long slot_elems) const {
@@ -520,6 +524,12 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
         const long long hi = pl->split_div > 0 ? pl->split_out_hi : 0;
         p.blk_bulk = bulk_ok && !split && kv.W == 1 && kv.S > 1 && ps.inner == 1 && pl->blk_out_inner == 1 && aligned &&
                      piece % 16 == 0 && (lo * (long long)(2 * sizeof(T))) % 16 == 0 && (hi * (long long)(2 * sizeof(T))) % 16 == 0;
+    }
+    if (pl->progress) {
+        if (!kv.progress) return fail(B2FFT_E_UNSUPPORTED, "kernel %s publishes no progress counters", kv.name);
+        p.progress = pl->progress;
+        p.progress_tiles = pl->progress_outer * p.inner_blocks;
+        p.max_ctas = pl->progress_max_ctas;
     }
     if (last && pl->exchange_max_ctas > 0) {
         p.max_ctas = pl->exchange_max_ctas;
@@ -830,6 +840,21 @@ int b2fft_plan_set_outer_split(b2fft_plan* plan, int64_t outer_div, int64_t in_s
     plan->split_div = outer_div;
     plan->split_in_lo = in_stride_lo; plan->split_in_hi = in_stride_hi;
     plan->split_out_lo = out_stride_lo; plan->split_out_hi = out_stride_hi;
+    return B2FFT_OK;
+}
+
+int b2fft_plan_set_progress(b2fft_plan* plan, void* counters, int64_t outer_per_chunk, int max_ctas, int64_t* target) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (target) *target = 0;
+    if (!counters) { plan->progress = nullptr; plan->progress_outer = 0; plan->progress_max_ctas = 0; return B2FFT_OK; }
+    if (outer_per_chunk <= 0 || max_ctas < 0) return fail(B2FFT_E_INVALID, "outer_per_chunk must be > 0 and max_ctas >= 0");
+    if (plan->passes.size() != 1) return fail(B2FFT_E_UNSUPPORTED, "progress counters need a single-pass plan");
+    const b2::KernelVariant& kv = registry().v[plan->passes[0].variant];
+    if (!kv.progress || !plan->fused_scratch) return fail(B2FFT_E_UNSUPPORTED, "kernel %s publishes no progress counters", kv.name);
+    plan->progress = (unsigned*)counters;
+    plan->progress_outer = outer_per_chunk;
+    plan->progress_max_ctas = max_ctas;
+    if (target) *target = outer_per_chunk * (plan->passes[0].inner / kv.W);
     return B2FFT_OK;
 }
 

@@ -262,6 +262,11 @@ struct PassParams {
     long long scratch_slots;  // number of super-tile slots the scratch buffer holds
     int fused_flags;          // bit 0: discard scratch lines after step B read them, 1: prefetch the next super-tile into L2,
                               // 2: evict-first policy on the DRAM streams, 3: evict-last policy on the scratch slot
+    // progress counters (fused2p kernel; slab pipeline): the CTA that has stored super-tile s adds 1 to
+    // progress[s / progress_tiles] with release semantics at device scope, so that a consumer on another stream can start
+    // on chunk k of the output while this launch is still working on the chunks behind it
+    unsigned* progress;       // nullptr: none
+    long long progress_tiles; // super-tiles per chunk
 };
 
 // ------------------------------------------------------------------ compile-time plan

@@ -697,6 +697,10 @@ __device__ __forceinline__ void b2_cp_async16(void* dst_smem, const void* src, u
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void b2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void b2_progress_add(unsigned* counter) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
 template <int PENDING>
 __device__ __forceinline__ void b2_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
@@ -795,6 +799,12 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
                 // and every other thread has seen the same for its own
                 b2_cp_async_wait<NSA - 1 - c>();
                 __syncthreads();
+                if constexpr (c == 0) {
+                    // every thread of the CTA has issued the stores of the previous super-tile: publish it (the barrier orders
+                    // their stores before this thread's fence, the fence is cumulative, the add is the release)
+                    if (pa.progress != nullptr && tid == 0 && s != (long long)blockIdx.x)
+                        b2_progress_add(pa.progress + (s - gridDim.x) / pa.progress_tiles);
+                }
                 fused2_setup_a<CfgA, CfgB>(th, tid, c, in_base, inner_in, 0);
                 fused2p_load_a<CfgA, CfgB, KS>(th, smem_i, cur);
                 th.template compute<0>(pa);
@@ -825,6 +835,10 @@ fused2p_fft_kernel(const __grid_constant__ PassParams<typename CfgA::T> pa, cons
         }
     }
     b2_cp_async_wait<0>();
+    if (pa.progress != nullptr && (long long)blockIdx.x < pa.n_tiles) {      // this CTA's last super-tile is s - gridDim.x
+        __syncthreads();
+        if (tid == 0) b2_progress_add(pa.progress + (s - gridDim.x) / pa.progress_tiles);
+    }
 }
 
 
@@ -915,6 +929,7 @@ struct KernelVariant {
     int radix_b[4];
     long long slot_elems;
     int (*grid_slots)();
+    int progress;    // 1: the kernel publishes per-chunk progress counters (PassParams::progress)
 };
 
 template <class Cfg, int MINB, bool BLKCAP = false, bool FSCAP = false>
@@ -1312,6 +1327,7 @@ struct VariantOpsFused2 {
     static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
         const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
         if (split || p.out_blk_log2 >= 0 || p.outer_div > 0 || !p.scratch || !p.fs_t2) return cudaErrorNotSupported;
+        if (p.progress != nullptr) return cudaErrorNotSupported;
         if (p.n_tiles <= 0) return cudaSuccess;
         if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
         long long ctas = p.n_tiles;
@@ -1402,6 +1418,7 @@ struct VariantOpsFused2S {
     static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
         const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
         if (split || p.out_blk_log2 >= 0 || p.outer_div > 0 || !p.scratch || !p.fs_t2) return cudaErrorNotSupported;
+        if (p.progress != nullptr && (!P || p.progress_tiles <= 0)) return cudaErrorNotSupported;
         if (p.n_tiles <= 0) return cudaSuccess;
         if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
         long long ctas = p.n_tiles;
@@ -1444,6 +1461,7 @@ struct VariantOpsFused2S {
         v.kind = 3;
         v.slot_elems = (long long)(CfgA::N - KS) * CfgB::N * CfgA::W;
         if (v.slot_elems == 0) v.slot_elems = CfgA::W;          // keep a (dummy) scratch allocation so that launch() runs
+        v.progress = P ? 1 : 0;
         v.launch = &launch;
         v.prepare = &prepare;
         v.occupancy = &occupancy;

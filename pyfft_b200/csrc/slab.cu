@@ -27,6 +27,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -103,6 +104,15 @@ struct b2fft_slab_plan {
     int G, rank, device, prec, C, K;
     size_t esz;
     b2fft_plan *fwd_y = nullptr, *fwd_x = nullptr, *fwd_z = nullptr;      // forward sub-plans
+    // overlap mode (b2fft_slab_plan_set_overlap): ONE Y launch over the whole slab on all but `overlap_sms` SMs with a
+    // progress counter per z-chunk; the X passes of chunk k wait for counter k instead of an event
+    b2fft_plan* fwd_y_all = nullptr;
+    void* ws_y_all = nullptr;
+    unsigned* d_progress = nullptr;
+    int overlap_sms = 0;
+    unsigned progress_target = 0;
+    int normalize = 1, fast_math = 1;
+    double scale = 1.0;
     b2fft_plan *inv_z = nullptr, *inv_x = nullptr, *inv_y = nullptr;      // inverse sub-plans
     void* ws[6] = {};                                                     // plan-owned workspaces of sub-plans that need one
     char* slab = nullptr;
@@ -163,7 +173,13 @@ int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int
     sp->X = X; sp->Y = Y; sp->Z = Z; sp->G = G; sp->rank = rank; sp->device = device; sp->prec = precision;
     sp->Zl = Z / G; sp->Xb = X / G;
     sp->esz = precision ? 16 : 8;
-    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : 1;
+    sp->normalize = normalize; sp->fast_math = fast_math; sp->scale = scale;
+    // default pipeline: 8 y-chunks; 8 z-chunks with the Y pass hidden under the exchange when that is possible and pays
+    // (>= 4 ranks: the exchange, not HBM, bounds the transform), else one z-chunk
+    int want_overlap = -1;
+    if (const char* e = getenv("B2FFT_SLAB_OVERLAP_SMS")) want_overlap = atoi(e);
+    const bool try_overlap = G > 1 && (want_overlap > 0 || (want_overlap < 0 && G >= 4));
+    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : (try_overlap ? 8 : 1);
     if (C > Y) C = Y;
     while (Y % C) --C;
     if (K > sp->Zl) K = sp->Zl;
@@ -219,7 +235,69 @@ int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int
         return fail_free(slab_fail(B2FFT_E_CUDA, "event creation: %s", cudaGetErrorString(e)));
     if ((e = cudaMalloc(&sp->d_err, sizeof(unsigned))) != cudaSuccess || (e = cudaMemset(sp->d_err, 0, sizeof(unsigned))) != cudaSuccess)
         return fail_free(slab_fail(B2FFT_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)));
+    if (try_overlap && sp->K > 1) {
+        rc = b2fft_slab_plan_set_overlap(sp, want_overlap > 0 ? want_overlap : -1);
+        if (rc != B2FFT_OK && rc != B2FFT_E_UNSUPPORTED) return fail_free(rc);
+        if (rc == B2FFT_E_UNSUPPORTED && z_chunks <= 0) {
+            // no hidden Y pass for these dimensions: z-chunks only add launches (profiles/r02_slab_pipeline.md)
+            sp->K = 1; sp->Zk = sp->Zl;
+            b2fft_plan_destroy(sp->fwd_y); b2fft_plan_destroy(sp->fwd_x);
+            sp->fwd_y = sp->fwd_x = nullptr;
+            if ((rc = mk(&sp->fwd_y, X, Y, sp->Zk, B2FFT_AXIS_Y, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+            if ((rc = mk(&sp->fwd_x, X, sp->Yc, sp->Zk, B2FFT_AXIS_X, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+            if (exchange_ctas_per_sm > 0 && (rc = b2fft_plan_set_exchange_ctas(sp->fwd_x, exchange_ctas_per_sm)) != B2FFT_OK)
+                return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+            size_t need = 0;
+            if ((rc = b2fft_plan_workspace_bytes_ex(sp->fwd_y, 1, 1, &need)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+            if (need) {
+                if (sp->ws[0]) { cudaFree(sp->ws[0]); sp->ws[0] = nullptr; }
+                if ((e = cudaMalloc(&sp->ws[0], need)) != cudaSuccess) return fail_free(slab_fail(B2FFT_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)));
+                if ((rc = b2fft_plan_set_workspace(sp->fwd_y, sp->ws[0], need)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+            }
+            for (size_t i = 1; i < sp->ev_y.size(); ++i) cudaEventDestroy(sp->ev_y[i]);
+            sp->ev_y.resize(1);
+        }
+    }
     *out = sp;
+    return B2FFT_OK;
+}
+
+int b2fft_slab_plan_set_overlap(b2fft_slab_plan* sp, int reserved_sms) {
+    if (!sp) return slab_fail(B2FFT_E_INVALID, "null plan");
+    DevGuard guard(sp->device);
+    if (reserved_sms == 0 || sp->K < 2 || (reserved_sms < 0 && sp->G < 2)) {
+        if (sp->fwd_y_all) { b2fft_plan_destroy(sp->fwd_y_all); sp->fwd_y_all = nullptr; }
+        sp->overlap_sms = 0;
+        return reserved_sms == 0 ? B2FFT_OK : slab_fail(B2FFT_E_UNSUPPORTED, "hiding the Y pass needs >= 2 z-chunks");
+    }
+    int sms = 0;
+    SLAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sp->device));
+    // default: the X pass runs 43 GB/s of rows per SM (profiles/r02_slab_pipeline.md), so ~40 SMs carry the 700 GB/s a
+    // GPU can store into its peers
+    int r = reserved_sms > 0 ? reserved_sms : (sms * 40) / 148;
+    if (r < 1) r = 1;
+    if (r > sms - 1) r = sms - 1;
+    if (!sp->fwd_y_all) {
+        const int64_t d[3] = {sp->X, sp->Y, sp->Zl};
+        const double nsize = (double)sp->X * (double)sp->Y * (double)sp->Z;
+        int rc = b2fft_plan_create_ex(&sp->fwd_y_all, d, B2FFT_AXIS_Y, sp->prec, B2FFT_INTERLEAVED, sp->normalize, sp->scale,
+                                      sp->fast_math, sp->device, nsize, 0);
+        if (rc != B2FFT_OK) return slab_fail(rc, "%s", b2fft_last_error());
+    }
+    if (!sp->d_progress) {
+        SLAB_CUDA(cudaMalloc(&sp->d_progress, 64 * sizeof(unsigned)));
+        SLAB_CUDA(cudaMemset(sp->d_progress, 0, 64 * sizeof(unsigned)));
+    }
+    int64_t target = 0;
+    int rc = sp->K <= 64 ? b2fft_plan_set_progress(sp->fwd_y_all, sp->d_progress, sp->Zk, sms - r, &target) : B2FFT_E_UNSUPPORTED;
+    if (rc != B2FFT_OK) {
+        std::string why = rc == B2FFT_E_UNSUPPORTED && sp->K > 64 ? "more than 64 z-chunks" : b2fft_last_error();
+        b2fft_plan_destroy(sp->fwd_y_all); sp->fwd_y_all = nullptr;
+        sp->overlap_sms = 0;
+        return slab_fail(rc, "%s", why.c_str());
+    }
+    sp->progress_target = (unsigned)target;                      // tiles per z-chunk
+    sp->overlap_sms = r;
     return B2FFT_OK;
 }
 
@@ -288,12 +366,27 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     SLAB_CUDA(cudaEventRecord(sp->ev_start, s));
     SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_start, 0));
     std::vector<void*> blk(G);
+    const bool overlap = sp->fwd_y_all != nullptr && sp->overlap_sms > 0;
+    if (overlap) {
+        // one persistent Y launch over the whole slab on all but overlap_sms SMs; counter k completes with z-chunk k
+        SLAB_CUDA(cudaMemsetAsync(sp->d_progress, 0, 64 * sizeof(unsigned), s));
+        SLAB_CUDA(cudaEventRecord(sp->ev_y[0], s));
+        SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[0], 0));
+        SLAB_TRY(b2fft_execute(sp->fwd_y_all, sp->slab, nullptr, sp->slab, nullptr, 0, 1, s));
+        sp->mark("Y_all", -1, -1, s);
+    }
     for (int k = 0; k < K; ++k) {
         char* zk = sp->slab + (size_t)k * sp->Zk * sp->Y * sp->X * esz;
-        SLAB_TRY(b2fft_execute(sp->fwd_y, zk, nullptr, zk, nullptr, 0, 1, s));
-        sp->mark("Y", k, -1, s);
-        SLAB_CUDA(cudaEventRecord(sp->ev_y[k], s));
-        SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[k], 0));
+        if (overlap) {
+            slab_wait_kernel<<<1, 32, 0, sp->sx>>>(sp->d_progress, k, 1, 1, sp->progress_target, sp->d_err, sp->timeout_cycles);
+            SLAB_CUDA(cudaGetLastError());
+            sp->mark("Y", k, -1, sp->sx);
+        } else {
+            SLAB_TRY(b2fft_execute(sp->fwd_y, zk, nullptr, zk, nullptr, 0, 1, s));
+            sp->mark("Y", k, -1, s);
+            SLAB_CUDA(cudaEventRecord(sp->ev_y[k], s));
+            SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[k], 0));
+        }
         if (k == 0 && G > 1) { SLAB_TRY(slab_wait(sp, sp->w_ready(0), 1, sp->epoch, sp->sx)); sp->mark("peers_ready", -1, -1, sp->sx); }
         for (int c = 0; c < C; ++c) {
             // rows {z in chunk k} x {y in chunk c}: row (z, y) starts at slab[(z*Y + y)*X]; its x-block h goes to
@@ -406,6 +499,7 @@ int64_t b2fft_slab_plan_launch_count(const b2fft_slab_plan* sp) {
     const b2fft_plan* subs[6] = {sp->fwd_y, sp->fwd_x, sp->fwd_z, sp->inv_z, sp->inv_x, sp->inv_y};
     for (auto* p : subs)
         if (p) n += b2fft_plan_launch_count(p);
+    if (sp->fwd_y_all) n += b2fft_plan_launch_count(sp->fwd_y_all);
     return n;
 }
 
@@ -419,8 +513,9 @@ int b2fft_slab_plan_describe(const b2fft_slab_plan* sp, char* buf, size_t buflen
         if (char* nl = strchr(s, '\n')) *nl = 0;
     snprintf(line, sizeof line,
              "rank %d/%d: z-slab [%lld][%lld][%lld] -> x-slab [%lld][%lld][%lld]; %d z-chunk(s) x %d y-chunk(s); "
-             "Y pass {%s} | X pass + NVLink-blocked stores {%s} | peer flags | Z pass {%s}",
-             sp->rank, sp->G, sp->Zl, sp->Y, sp->X, sp->Y, sp->Z, sp->Xb, sp->K, sp->C, a, b, c);
+             "Y pass {%s}%s | X pass + NVLink-blocked stores {%s} | peer flags | Z pass {%s}",
+             sp->rank, sp->G, sp->Zl, sp->Y, sp->X, sp->Y, sp->Z, sp->Xb, sp->K, sp->C, a,
+             sp->overlap_sms > 0 ? " as one launch with per-chunk progress counters, hidden under the exchange" : "", b, c);
     snprintf(buf, buflen, "%s", line);
     return B2FFT_OK;
 }
@@ -431,6 +526,9 @@ int b2fft_slab_plan_destroy(b2fft_slab_plan* sp) {
     b2fft_plan* subs[6] = {sp->fwd_y, sp->fwd_x, sp->fwd_z, sp->inv_z, sp->inv_x, sp->inv_y};
     for (auto* p : subs)
         if (p) b2fft_plan_destroy(p);
+    if (sp->fwd_y_all) b2fft_plan_destroy(sp->fwd_y_all);
+    if (sp->ws_y_all) cudaFree(sp->ws_y_all);
+    if (sp->d_progress) cudaFree(sp->d_progress);
     for (void* w : sp->ws)
         if (w) cudaFree(w);
     if (sp->sx) cudaStreamDestroy(sp->sx);

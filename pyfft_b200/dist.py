@@ -149,7 +149,8 @@ class SlabPlan(object):
     """
 
     def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
-                 exchange="xslab", device=None, yslab_layout="zyx", chunks=1, exchange_ctas_per_sm=3, z_chunks=1):
+                 exchange="xslab", device=None, yslab_layout="zyx", chunks=1, exchange_ctas_per_sm=3, z_chunks=0,
+                 overlap_sms=None):
         import torch
         import torch.distributed as dist
         if len(shape) != 3:
@@ -165,7 +166,10 @@ class SlabPlan(object):
         # chunk c runs on a side stream while the X/Y passes of chunk c+1 compute
         self.chunks = max(1, int(chunks))
         self.exchange_ctas_per_sm = int(exchange_ctas_per_sm)
-        self.z_chunks = max(1, int(z_chunks))
+        # x-slab mode: z_chunks = 0 lets the native plan choose (8 with the Y pass hidden under the exchange where that is
+        # possible, else 1); overlap_sms: SMs left to the exchange while the Y pass runs (None = default, 0 = off)
+        self.z_chunks = max(0, int(z_chunks))
+        self.overlap_sms = overlap_sms
         self._normalize, self._scale, self._fast_math = bool(normalize), float(scale), bool(fast_math)
         self._native = None
         self._torch, self._dist = torch, dist
@@ -268,6 +272,10 @@ class SlabPlan(object):
                                                self.chunks if self.chunks > 1 else 0, self.z_chunks,
                                                self.exchange_ctas_per_sm if G > 1 else 0))
         self._native = h
+        if self.overlap_sms is not None:
+            rc = lib.b2fft_slab_plan_set_overlap(h, int(self.overlap_sms))
+            if rc not in (_lib.OK, _lib.E_UNSUPPORTED):
+                self._check(rc)
         geo = (ctypes.c_int64 * 8)()
         self._check(lib.b2fft_slab_plan_geometry(h, geo))
         self.chunks, self.z_chunks = int(geo[2]), int(geo[3])

@@ -65,6 +65,36 @@ def test_xslab_plan_single_rank(cuda_device, shape, dtype, chunks, z_chunks):
     plan.close()
 
 
+def test_xslab_plan_hidden_y_pass_single_rank(cuda_device):
+    """Overlap mode of the native slab plan (b2fft_slab_plan_set_overlap): the Y pass of a 2048-long axis is ONE persistent
+    launch (streamed fused two-step kernel) on all but 40 SMs that publishes a progress counter per z-chunk; the X
+    passes of z-chunk k wait for counter k on another stream.  Same result as the event-ordered schedule, repeatedly
+    (the counters are re-armed every call)."""
+    import torch
+    from pyfft_b200.dist import SlabPlan
+    shape, dtype = (16, 2048, 64), np.complex64
+    plan = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=4, z_chunks=4, overlap_sms=40)
+    assert "hidden under the exchange" in plan.describe() and "_fused2p" in plan.describe()
+    ref = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=4, z_chunks=4, overlap_sms=0)
+    assert "hidden under the exchange" not in ref.describe()
+    x = no.make_input(shape, 1, dtype, seed=29)[0]
+    want = np.fft.fftn(x.astype(np.complex128))
+    tol = no.tolerance(dtype, int(np.prod(shape)))
+    for _ in range(3):
+        plan.slab.copy_(torch.from_numpy(x).to(cuda_device))
+        ref.slab.copy_(torch.from_numpy(x).to(cuda_device))
+        y, yr = plan.forward(), ref.forward()
+        torch.cuda.synchronize()
+        assert no.rel_l2(y.cpu().numpy().transpose(1, 0, 2), want) < tol
+        assert torch.equal(y, yr)                    # same kernels on the same data: bit-identical
+        back = plan.inverse()
+        torch.cuda.synchronize()
+        assert no.rel_l2(back.cpu().numpy(), x) < tol
+    assert plan.status() == 0
+    plan.close()
+    ref.close()
+
+
 def test_batch_sharded_plan_single_rank(cuda_device):
     import torch
     from pyfft_b200.dist import BatchShardedPlan
@@ -88,3 +118,11 @@ def test_slab_two_ranks_if_available(cuda_device):
     assert len(recs) == 14
     for r in recs:
         assert r["fwd_rel_l2"] < 1e-5 * 21 and r["roundtrip_rel_l2"] < 1e-5 * 21 and r["delta_max_err"] < 1e-4, r
+    # the Y pass hidden under the exchange (progress counters instead of events), 2048-long Y axis, against the plain schedule
+    cmd = cmd[:cmd.index("--size")] + ["--shape", "32,2048,64", "--check", "--steps", "0", "--exchange", "xslabx4z4o40", "xslabx4z4o0"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    recs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(recs) == 2 and "hidden under the exchange" in recs[0]["describe"] and "hidden" not in recs[1]["describe"]
+    for r in recs:
+        assert r["fwd_rel_l2"] < 1e-5 * 22 and r["roundtrip_rel_l2"] < 1e-5 * 22 and r["delta_max_err"] < 1e-4 and r["status"] == 0, r

@@ -23,7 +23,8 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--size", dest="n", type=int, nargs="+", default=[256])
+    ap.add_argument("--size", dest="n", type=int, nargs="*", default=None)
+    ap.add_argument("--shape", nargs="*", default=[], help="Z,Y,X (non-cubic arrays), e.g. 16,2048,64")
     ap.add_argument("--exchange", nargs="+", default=["p2p", "nccl"], help="p2p | nccl | p2p-yzx ([Yb][Z][X] y-slab layout)")
     ap.add_argument("--dtype", default="complex64")
     ap.add_argument("--steps", type=int, default=5)
@@ -42,25 +43,30 @@ def main():
     from pyfft_b200.dist import SlabPlan
     npdt = np.dtype(args.dtype)
     results = []
-    for n in args.n:
-        shape = (n, n, n)
+    shapes = [(n, n, n) for n in (args.n if args.n is not None else ([] if args.shape else [256]))]
+    shapes += [tuple(int(v) for v in sh.split(",")) for sh in args.shape]
+    for shape in shapes:
+        n = shape[0] if shape[0] == shape[1] == shape[2] else list(shape)
+        nz, ny, nx = shape
         for ex in args.exchange:
             if world == 1 and ex != args.exchange[0]:
                 continue
             yzx = ex.endswith("-yzx")
             chunks = int(ex.split("x")[1]) if ex.startswith("ncclx") else 1          # "ncclx8" = 8 pipelined chunks
             xs = ex.startswith("xslab")               # "xslab[xC][zK][cN]": C y-chunks, K z-chunks, N exchange CTAs per SM
-            ctas, zch = 3, 1
-            if xs:
+            ctas, zch, ovl = 3, 0, None
+            if xs:       # "xslab[xC][zK][cN][oR]": ... R SMs left to the exchange while the Y pass runs (o0 = Y pass not hidden)
                 import re
-                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?$", ex)
+                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?(?:o(\d+))?$", ex)
                 if not m:
                     raise SystemExit("bad exchange spec " + ex)
                 chunks = int(m.group(1)) if m.group(1) else 8
-                zch = int(m.group(2)) if m.group(2) else 1
+                zch = int(m.group(2)) if m.group(2) else 0
                 ctas = int(m.group(3)) if m.group(3) else 3
+                ovl = int(m.group(4)) if m.group(4) else None
             plan = SlabPlan(shape, dtype=npdt, exchange="xslab" if xs else "nccl" if ex.startswith("nccl") else ex.split("-")[0],
-                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas, z_chunks=zch)
+                            yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas, z_chunks=zch,
+                            overlap_sms=ovl)
             L = plan.L
             g = torch.Generator(device=dev)
             g.manual_seed(4242 + rank)
@@ -70,11 +76,12 @@ def main():
                 zs = max(1, L["Zl"] // 16)
                 for z0 in range(0, L["Zl"], zs):          # in pieces: no slab-sized temporaries
                     z1 = min(L["Zl"], z0 + zs)
-                    plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, n, n, 2, dtype=fl, device=dev, generator=g)))
+                    plan.slab[z0:z1].copy_(torch.view_as_complex(torch.randn(z1 - z0, ny, nx, 2, dtype=fl, device=dev, generator=g)))
             rec = {"n": n, "world": world, "exchange": ex, "dtype": args.dtype,
-                   "y_chunks": plan.chunks, "z_chunks": getattr(plan, "z_chunks", 1)}
+                   "y_chunks": plan.chunks, "z_chunks": getattr(plan, "z_chunks", 1),
+                   "describe": plan.describe()[:400] if hasattr(plan, "describe") else ""}
             fill()
-            x_local = plan.slab.clone() if (args.check or n <= 1024) else None
+            x_local = plan.slab.clone() if (args.check or nz * ny * nx <= 1024 ** 3) else None
             energy_in = float((plan.slab.abs() ** 2).sum().double().item())
             plan.forward()
             torch.cuda.synchronize()
@@ -84,7 +91,7 @@ def main():
                 dist.all_reduce(t)
                 energy_in, energy_out = t.tolist()
             # Parseval: sum|X|^2 = N * sum|x|^2
-            rec["parseval_rel_err"] = abs(energy_out / (energy_in * n ** 3) - 1.0)
+            rec["parseval_rel_err"] = abs(energy_out / (energy_in * float(nz * ny * nx)) - 1.0)
             if args.check:
                 if world > 1:      # NCCL has no complex dtype: gather the (re, im) views
                     xr, yr = torch.view_as_real(x_local).contiguous(), torch.view_as_real(plan.yslab).contiguous()
@@ -144,7 +151,7 @@ def main():
                     t = torch.tensor([ms], dtype=torch.float64, device=dev)
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                     ms = float(t.item())
-                N = float(n) ** 3
+                N = float(nz) * ny * nx
                 if hasattr(plan, "set_trace") and os.environ.get("SLAB_TRACE"):
                     plan.set_trace(True)
                     plan.forward()
