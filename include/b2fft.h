@@ -140,6 +140,12 @@ B2FFT_API int b2fft_plan_set_exchange_ctas(b2fft_plan* plan, int ctas_per_sm);
  * consumer.  B2FFT_E_UNSUPPORTED if the plan's kernel cannot do it; counters = NULL switches it off. */
 B2FFT_API int b2fft_plan_set_progress(b2fft_plan* plan, void* counters, int64_t outer_per_chunk, int max_ctas, int64_t* target);
 
+/* Caps the grid of every pass of the plan whose kernel walks its tiles with a grid stride (the plain and the fused
+ * two-step kernels; the TMA-staged persistent kernels size their own grid and ignore it) at max_ctas CTAs, so that a
+ * kernel on another stream finds free SMs beside it (slab pipeline: the Z passes leave room for the NVLink-bound X pass).
+ * 0 = no cap. */
+B2FFT_API int b2fft_plan_set_max_ctas(b2fft_plan* plan, int max_ctas);
+
 /* Peer-visible device memory for the slab exchange: plain cudaMalloc'ed buffers whose CUDA IPC
  * handles (64 bytes) can be exchanged between the per-GPU processes (e.g. through
  * torch.distributed.all_gather_object) and opened on the other ranks. */
@@ -187,6 +193,9 @@ B2FFT_API int b2fft_slab_plan_attach(b2fft_slab_plan* plan, void* slab, void* co
  * progress counters, B2FFT_SLAB_OVERLAP_SMS overrides).  Returns B2FFT_E_UNSUPPORTED (and stays off) when the Y pass of
  * these dimensions cannot publish progress.  Call before the first forward. */
 B2FFT_API int b2fft_slab_plan_set_overlap(b2fft_slab_plan* plan, int reserved_sms);
+/* Tuning knobs of the pipeline.  "overlap_columns": how many y-chunks are sent z-chunk by z-chunk while the hidden Y launch
+ * is still running (the rest go out one y-chunk at a time over all z); 0 = default (3/8 of the y-chunks). */
+B2FFT_API int b2fft_slab_plan_set_option(b2fft_slab_plan* plan, const char* key, double value);
 B2FFT_API int b2fft_slab_forward(b2fft_slab_plan* plan, void* cuda_stream);
 B2FFT_API int b2fft_slab_inverse(b2fft_slab_plan* plan, void* cuda_stream);
 /* 0 = healthy; non-zero = a cross-rank wait timed out (a peer never signalled); synchronises the device */
@@ -228,7 +237,9 @@ B2FFT_API int b2fft_run_variant(int index, const void* in0, const void* in1, voi
  * plans are created afterwards ("" clears).  Also read from $B2FFT_PREFER at load time. */
 B2FFT_API int b2fft_set_preferred_variants(const char* names);
 
-/* Global tuning options.  "l2_chunk_bytes": multi-pass transforms run their passes chunk by
+/* Global tuning options.  "blk_bulk": how the destination-blocked stores of a contiguous-axis pass (slab exchange) leave
+ * the SM: 0 = warp stores, 1 = TMA bulk copies staged in the exchange buffer, 2 = bulk copies from a staging buffer of
+ * their own, so that they drain while the CTA transforms its next lines (also $B2FFT_BLK_BULK).  "l2_chunk_bytes": multi-pass transforms run their passes chunk by
  * chunk so the intermediate stays in the 126 MB L2 between passes (bytes; default 0 = whole-array
  * passes, also settable through $B2FFT_L2_CHUNK_MB). */
 B2FFT_API int b2fft_set_option(const char* key, double value);

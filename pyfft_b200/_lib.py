@@ -48,8 +48,10 @@ SIGNATURES = {
     "b2fft_slab_last_error": (ctypes.c_char_p, []),
     "b2fft_plan_set_outer_split": (_i, [_vp, _i64, _i64, _i64, _i64, _i64]),
     "b2fft_plan_set_exchange_ctas": (_i, [_vp, _i]),
+    "b2fft_plan_set_max_ctas": (_i, [_vp, _i]),
     "b2fft_plan_set_progress": (_i, [_vp, _vp, _i64, _i, ctypes.POINTER(_i64)]),
     "b2fft_slab_plan_set_overlap": (_i, [_vp, _i]),
+    "b2fft_slab_plan_set_option": (_i, [_vp, ctypes.c_char_p, _d]),
     "b2fft_mem_alloc": (_i, [_sz, _i, ctypes.POINTER(_vp)]),
     "b2fft_mem_free": (_i, [_vp]),
     "b2fft_ipc_export": (_i, [_vp, ctypes.c_char_p]),

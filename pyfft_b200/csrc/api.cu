@@ -28,6 +28,10 @@ thread_local std::string g_err;
 // pass wrote is still in the 126 MB L2 when the next pass reads it (0 disables).  Measured on
 // B200 (profiles/r01_l2_chunking.md): with one kernel launch per chunk and pass the launch/drain
 // overhead of the many short kernels outweighs the saved DRAM traffic, so the default is off.
+// Destination-blocked stores of contiguous-axis passes (slab exchange) as TMA bulk copies: 0 = warp stores, 1 = bulk copies
+// staged in the exchange buffer (the CTA waits for them), 2 = bulk copies from a staging buffer of their own (they drain
+// while the CTA works on its next lines).  $B2FFT_BLK_BULK / b2fft_set_option("blk_bulk").
+std::atomic<int> g_blk_bulk_mode{[] { const char* e = getenv("B2FFT_BLK_BULK"); return e ? atoi(e) : 1; }()};
 std::atomic<long long> g_l2_chunk_bytes{[] {
     const char* e = getenv("B2FFT_L2_CHUNK_MB");
     return (long long)((e ? atof(e) : 0.0) * 1024.0 * 1024.0);
@@ -311,6 +315,7 @@ struct b2fft_plan {
     unsigned* progress = nullptr;
     long long progress_outer = 0;
     int progress_max_ctas = 0;
+    int max_ctas = 0;            // grid cap of every pass whose kernel strides over its tiles (b2fft_plan_set_max_ctas)
     long long split_div = 0, split_in_lo = 0, split_in_hi = 0, split_out_lo = 0, split_out_hi = 0;
     std::atomic<long long> launches{0};
     long long fused_slots_for(long long slot_elems) const {
@@ -522,9 +527,11 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
         const long long piece = (ps.n / pl->nblocks) * (long long)(2 * sizeof(T));
         const long long lo = pl->split_div > 0 ? pl->split_out_lo : pl->blk_out_outer_stride;
         const long long hi = pl->split_div > 0 ? pl->split_out_hi : 0;
-        p.blk_bulk = bulk_ok && !split && kv.W == 1 && kv.S > 1 && ps.inner == 1 && pl->blk_out_inner == 1 && aligned &&
-                     piece % 16 == 0 && (lo * (long long)(2 * sizeof(T))) % 16 == 0 && (hi * (long long)(2 * sizeof(T))) % 16 == 0;
+        p.blk_bulk = (bulk_ok && !split && kv.W == 1 && kv.S > 1 && ps.inner == 1 && pl->blk_out_inner == 1 && aligned &&
+                     piece % 16 == 0 && (lo * (long long)(2 * sizeof(T))) % 16 == 0 && (hi * (long long)(2 * sizeof(T))) % 16 == 0)
+                        ? g_blk_bulk_mode.load() : 0;
     }
+    if (pl->max_ctas > 0 && (kv.kind == 0 || kv.kind == 3)) p.max_ctas = pl->max_ctas;
     if (pl->progress) {
         if (!kv.progress) return fail(B2FFT_E_UNSUPPORTED, "kernel %s publishes no progress counters", kv.name);
         p.progress = pl->progress;
@@ -858,6 +865,13 @@ int b2fft_plan_set_progress(b2fft_plan* plan, void* counters, int64_t outer_per_
     return B2FFT_OK;
 }
 
+int b2fft_plan_set_max_ctas(b2fft_plan* plan, int max_ctas) {
+    if (!plan) return fail(B2FFT_E_INVALID, "null plan");
+    if (max_ctas < 0) return fail(B2FFT_E_INVALID, "max_ctas must be >= 0");
+    plan->max_ctas = max_ctas;
+    return B2FFT_OK;
+}
+
 int b2fft_plan_set_exchange_ctas(b2fft_plan* plan, int ctas_per_sm) {
     if (!plan) return fail(B2FFT_E_INVALID, "null plan");
     if (ctas_per_sm < 0) return fail(B2FFT_E_INVALID, "ctas_per_sm must be >= 0");
@@ -1014,6 +1028,11 @@ int b2fft_run_variant(int index, const void* in0, const void* in1, void* out0, v
 
 int b2fft_set_option(const char* key, double value) {
     if (!key) return fail(B2FFT_E_INVALID, "null key");
+    if (!strcmp(key, "blk_bulk")) {
+        if (value != 0 && value != 1 && value != 2) return fail(B2FFT_E_INVALID, "blk_bulk must be 0, 1 or 2");
+        g_blk_bulk_mode.store((int)value);
+        return B2FFT_OK;
+    }
     if (!strcmp(key, "l2_chunk_bytes")) {
         if (value < 0) return fail(B2FFT_E_INVALID, "l2_chunk_bytes must be >= 0");
         g_l2_chunk_bytes.store((long long)value);

@@ -47,7 +47,13 @@ __device__ __forceinline__ void store_blocked_bulk(TileThread<Cfg, false, INV, f
     using T2 = vec2<T>;
     constexpr int N = Cfg::N, TPC = Cfg::TPC, S = Cfg::S;
     constexpr int R = Cfg::R(S - 1), LG = ilog2(R), BPT = Cfg::BPT(S - 1);
-    __syncthreads();                                   // the last exchange has been read by everyone
+    // blk_bulk == 2: the lines are staged in a buffer of their own behind the exchange buffer, so the copies of one group of
+    // lines drain (over NVLink) while the CTA already loads and transforms the next group; only the staging buffer has
+    // to wait for them.  blk_bulk == 1: staged in the exchange buffer itself, the CTA waits for the copies before it goes on.
+    const bool own = p.blk_bulk == 2;
+    if (own) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous group's copies have read the staging buffer
+    __syncthreads();                                   // ... for every issuing thread / the last exchange has been read by everyone
+    smem += own ? (long long)Cfg::COL_SMEM * Cfg::W * Cfg::G : 0;
     th.apply_scale(p);
     if (th.active) {
         T2* dst = smem + (long long)th.g * N + th.t;
@@ -76,7 +82,7 @@ __device__ __forceinline__ void store_blocked_bulk(TileThread<Cfg, false, INV, f
         }
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused (after a barrier)
+    if (!own) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused (after a barrier)
 }
 
 // Four-step pass A on a contiguous axis (inner0 == 1): column w of the tile becomes the N1 contiguous
@@ -938,8 +944,12 @@ struct VariantOps {
     template <bool SPLIT, bool INV, bool BLK, bool FS>
     static cudaError_t attr() {
         return cudaFuncSetAttribute(tile_fft_kernel<Cfg, SPLIT, INV, MINB, BLK, FS>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((BLK && BLK_OWN_OK) ? BLK_SMEM : Cfg::SMEM_BYTES));
     }
+    // blocked bulk stores with their own staging buffer (PassParams::blk_bulk == 2): G dense lines behind the exchange buffer
+    static constexpr size_t STAGE_BYTES = (size_t)Cfg::G * Cfg::N * Cfg::W * 2 * sizeof(T);
+    static constexpr size_t BLK_SMEM = (size_t)Cfg::SMEM_BYTES + STAGE_BYTES;
+    static constexpr bool BLK_OWN_OK = BLK_SMEM * MINB <= 200 * 1024;
     template <bool BLK, bool FS>
     static cudaError_t attr3() {
         cudaError_t e;
@@ -949,8 +959,11 @@ struct VariantOps {
     }
     static cudaError_t prepare() {
         cudaError_t e = cudaSuccess;
+        if constexpr (BLKCAP) {
+            if (BLK_SMEM > 48 * 1024 && BLK_OWN_OK) { if ((e = attr3<true, false>()) != cudaSuccess) return e; }
+        }
         if (Cfg::SMEM_BYTES > 48 * 1024) {
-            if constexpr (BLKCAP) { if ((e = attr3<true, false>()) != cudaSuccess) return e; }
+            if constexpr (BLKCAP) { if (!BLK_OWN_OK && (e = attr3<true, false>()) != cudaSuccess) return e; }
             if constexpr (FSCAP) { if ((e = attr3<false, true>()) != cudaSuccess) return e; }
             e = attr3<false, false>();
         }
@@ -970,8 +983,17 @@ struct VariantOps {
         const dim3 grid((unsigned)((p.max_ctas > 0 && ctas > p.max_ctas) ? p.max_ctas : ctas)), block(Cfg::THREADS);
         const size_t sm = (size_t)Cfg::SMEM_BYTES;
         if (p.out_blk_log2 >= 0) {
-            if constexpr (BLKCAP) go<true, false>(split, inv, grid, block, sm, stream, p);
-            else return cudaErrorNotSupported;
+            if constexpr (BLKCAP) {
+                if (p.blk_bulk == 2 && BLK_OWN_OK) {
+                    go<true, false>(split, inv, grid, block, BLK_SMEM, stream, p);
+                } else if (p.blk_bulk == 2) {
+                    PassParams<T> q = p;
+                    q.blk_bulk = 1;
+                    go<true, false>(split, inv, grid, block, sm, stream, q);
+                } else {
+                    go<true, false>(split, inv, grid, block, sm, stream, p);
+                }
+            } else return cudaErrorNotSupported;
         } else if (p.fs_t1 != nullptr) {
             if constexpr (FSCAP) go<false, true>(split, inv, grid, block, sm, stream, p);
             else return cudaErrorNotSupported;

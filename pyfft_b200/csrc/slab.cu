@@ -107,6 +107,9 @@ struct b2fft_slab_plan {
     // overlap mode (b2fft_slab_plan_set_overlap): ONE Y launch over the whole slab on all but `overlap_sms` SMs with a
     // progress counter per z-chunk; the X passes of chunk k wait for counter k instead of an event
     b2fft_plan* fwd_y_all = nullptr;
+    b2fft_plan* fwd_x_all = nullptr;      // X pass of {all local z} x {one y-chunk}: the columns sent after the Y pass has finished
+    int exchange_ctas_per_sm = 0;
+    int overlap_columns = 0;              // y-chunks sent z-chunk by z-chunk while the Y launch runs (0 = default, 3/8 of them)
     void* ws_y_all = nullptr;
     unsigned* d_progress = nullptr;
     int overlap_sms = 0;
@@ -174,12 +177,13 @@ int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int
     sp->Zl = Z / G; sp->Xb = X / G;
     sp->esz = precision ? 16 : 8;
     sp->normalize = normalize; sp->fast_math = fast_math; sp->scale = scale;
-    // default pipeline: 8 y-chunks; 8 z-chunks with the Y pass hidden under the exchange when that is possible and pays
+    sp->exchange_ctas_per_sm = G > 1 ? exchange_ctas_per_sm : 0;
+    // default pipeline: 8 y-chunks; 4 z-chunks with the Y pass hidden under the exchange when that is possible and pays
     // (>= 4 ranks: the exchange, not HBM, bounds the transform), else one z-chunk
     int want_overlap = -1;
     if (const char* e = getenv("B2FFT_SLAB_OVERLAP_SMS")) want_overlap = atoi(e);
     const bool try_overlap = G > 1 && (want_overlap > 0 || (want_overlap < 0 && G >= 4));
-    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : (try_overlap ? 8 : 1);
+    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : (try_overlap ? 4 : 1);
     if (C > Y) C = Y;
     while (Y % C) --C;
     if (K > sp->Zl) K = sp->Zl;
@@ -267,6 +271,8 @@ int b2fft_slab_plan_set_overlap(b2fft_slab_plan* sp, int reserved_sms) {
     DevGuard guard(sp->device);
     if (reserved_sms == 0 || sp->K < 2 || (reserved_sms < 0 && sp->G < 2)) {
         if (sp->fwd_y_all) { b2fft_plan_destroy(sp->fwd_y_all); sp->fwd_y_all = nullptr; }
+        if (sp->fwd_x_all) { b2fft_plan_destroy(sp->fwd_x_all); sp->fwd_x_all = nullptr; }
+        if (sp->fwd_z) b2fft_plan_set_max_ctas(sp->fwd_z, 0);
         sp->overlap_sms = 0;
         return reserved_sms == 0 ? B2FFT_OK : slab_fail(B2FFT_E_UNSUPPORTED, "hiding the Y pass needs >= 2 z-chunks");
     }
@@ -297,8 +303,34 @@ int b2fft_slab_plan_set_overlap(b2fft_slab_plan* sp, int reserved_sms) {
         return slab_fail(rc, "%s", why.c_str());
     }
     sp->progress_target = (unsigned)target;                      // tiles per z-chunk
+    // the columns that leave after the Y pass has finished go out as one launch over all local z
+    if (!sp->fwd_x_all) {
+        const int64_t d[3] = {sp->X, sp->Yc, sp->Zl};
+        const double nsize = (double)sp->X * (double)sp->Y * (double)sp->Z;
+        rc = b2fft_plan_create_ex(&sp->fwd_x_all, d, B2FFT_AXIS_X, sp->prec, B2FFT_INTERLEAVED, sp->normalize, sp->scale, sp->fast_math,
+                                  sp->device, nsize, 0);
+        if (rc == B2FFT_OK && sp->exchange_ctas_per_sm > 0) rc = b2fft_plan_set_exchange_ctas(sp->fwd_x_all, sp->exchange_ctas_per_sm);
+        if (rc != B2FFT_OK) {
+            std::string why = b2fft_last_error();
+            if (sp->fwd_x_all) { b2fft_plan_destroy(sp->fwd_x_all); sp->fwd_x_all = nullptr; }
+            b2fft_plan_destroy(sp->fwd_y_all); sp->fwd_y_all = nullptr;
+            return slab_fail(rc, "%s", why.c_str());
+        }
+    }
+    // the Z passes run beside the exchange of the following columns: they leave it the same SMs
+    if ((rc = b2fft_plan_set_max_ctas(sp->fwd_z, sms - r)) != B2FFT_OK) return slab_fail(rc, "%s", b2fft_last_error());
     sp->overlap_sms = r;
     return B2FFT_OK;
+}
+
+int b2fft_slab_plan_set_option(b2fft_slab_plan* sp, const char* key, double value) {
+    if (!sp || !key) return slab_fail(B2FFT_E_INVALID, "null argument");
+    if (!strcmp(key, "overlap_columns")) {
+        if (value < 0 || value > sp->C) return slab_fail(B2FFT_E_INVALID, "overlap_columns must be in [0, y_chunks]");
+        sp->overlap_columns = (int)value;
+        return B2FFT_OK;
+    }
+    return slab_fail(B2FFT_E_INVALID, "unknown slab option %s", key);
 }
 
 int b2fft_slab_plan_sizes(const b2fft_slab_plan* sp, size_t* slab_bytes, size_t* xslab_bytes, size_t* flag_bytes) {
@@ -375,42 +407,60 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
         SLAB_TRY(b2fft_execute(sp->fwd_y_all, sp->slab, nullptr, sp->slab, nullptr, 0, 1, s));
         sp->mark("Y_all", -1, -1, s);
     }
-    for (int k = 0; k < K; ++k) {
+    // Order of the (z-chunk k, y-chunk c) cells of the X pass.  Z pass c needs column c complete, cell (k, c) needs the Y
+    // pass of z-chunk k.  Event-ordered Y passes: k-major (the Y pass of chunk k+1 runs beside the cells of chunk k).
+    // Hidden Y pass: the first C1 columns k-major while the Y launch works its way through the z-chunks (they take about as
+    // long as the Y pass, so the cells rarely wait), then the other columns one after the other, each as one launch over
+    // all z, so that the Z passes start early, spread out and hide under the stores of the following columns.
+    std::vector<std::pair<int, int>> cells;                      // k = -1: all z-chunks of the column in one launch
+    // the z-chunk-major part has to last about as long as the Y launch (4.5 of the 13 ms of X work at 2048^3 on 8 GPUs): 3/8
+    const int C1 = !overlap ? C : sp->overlap_columns > 0 ? (sp->overlap_columns < C ? sp->overlap_columns : C) : (3 * C + 7) / 8;
+    for (int k = 0; k < K; ++k)
+        for (int c = 0; c < C1; ++c) cells.emplace_back(k, c);
+    for (int c = C1; c < C; ++c) cells.emplace_back(-1, c);
+    std::vector<int> done_in_column(C, 0);
+    int y_ready = -1;                                            // z-chunks whose Y pass the exchange stream has waited for
+    for (const auto& cell : cells) {
+        const bool whole = cell.first < 0;
+        const int k = whole ? 0 : cell.first, c = cell.second;
+        b2fft_plan* xp = whole ? sp->fwd_x_all : sp->fwd_x;
         char* zk = sp->slab + (size_t)k * sp->Zk * sp->Y * sp->X * esz;
-        if (overlap) {
-            slab_wait_kernel<<<1, 32, 0, sp->sx>>>(sp->d_progress, k, 1, 1, sp->progress_target, sp->d_err, sp->timeout_cycles);
-            SLAB_CUDA(cudaGetLastError());
-            sp->mark("Y", k, -1, sp->sx);
-        } else {
-            SLAB_TRY(b2fft_execute(sp->fwd_y, zk, nullptr, zk, nullptr, 0, 1, s));
-            sp->mark("Y", k, -1, s);
-            SLAB_CUDA(cudaEventRecord(sp->ev_y[k], s));
-            SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[k], 0));
-        }
-        if (k == 0 && G > 1) { SLAB_TRY(slab_wait(sp, sp->w_ready(0), 1, sp->epoch, sp->sx)); sp->mark("peers_ready", -1, -1, sp->sx); }
-        for (int c = 0; c < C; ++c) {
-            // rows {z in chunk k} x {y in chunk c}: row (z, y) starts at slab[(z*Y + y)*X]; its x-block h goes to
-            // xslab_h[(y*Z + rank*Zl + z)*Xb]
-            char* src = zk + (size_t)c * sp->Yc * sp->X * esz;
-            for (int h = 0; h < G; ++h)
-                blk[h] = sp->xslab[h] + ((size_t)c * sp->Yc * sp->Z + (size_t)sp->rank * sp->Zl + (size_t)k * sp->Zk) * sp->Xb * esz;
-            SLAB_TRY(b2fft_plan_set_output_blocks(sp->fwd_x, G, blk.data(), nullptr, 1, sp->Z * sp->Xb));
-            SLAB_TRY(b2fft_plan_set_outer_split(sp->fwd_x, sp->Yc, sp->X, sp->Y * sp->X, sp->Z * sp->Xb, sp->Xb));
-            SLAB_TRY(b2fft_execute(sp->fwd_x, src, nullptr, src, nullptr, 0, 1, sp->sx));
-            sp->mark("X", k, c, sp->sx);
-            if (k == K - 1) {
-                if (G > 1) {
-                    SLAB_TRY(slab_signal(sp, sp->w_chunk(sp->rank, c), sp->sx));
-                    SLAB_TRY(slab_wait(sp, sp->w_chunk(0, c), C, sp->epoch, sp->sz));
-                    sp->mark("chunk_arrived", c, -1, sp->sz);
-                } else {
-                    SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
-                    SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_sx, 0));
-                }
-                char* zc = sp->xslab[sp->rank] + (size_t)c * sp->Yc * sp->Z * sp->Xb * esz;
-                SLAB_TRY(b2fft_execute(sp->fwd_z, zc, nullptr, zc, nullptr, 0, 1, sp->sz));
-                sp->mark("Z", c, -1, sp->sz);
+        while (y_ready < (whole ? K - 1 : k)) {
+            ++y_ready;
+            char* zy = sp->slab + (size_t)y_ready * sp->Zk * sp->Y * sp->X * esz;
+            if (overlap) {
+                slab_wait_kernel<<<1, 32, 0, sp->sx>>>(sp->d_progress, y_ready, 1, 1, sp->progress_target, sp->d_err, sp->timeout_cycles);
+                SLAB_CUDA(cudaGetLastError());
+                sp->mark("Y", y_ready, -1, sp->sx);
+            } else {
+                SLAB_TRY(b2fft_execute(sp->fwd_y, zy, nullptr, zy, nullptr, 0, 1, s));
+                sp->mark("Y", y_ready, -1, s);
+                SLAB_CUDA(cudaEventRecord(sp->ev_y[y_ready], s));
+                SLAB_CUDA(cudaStreamWaitEvent(sp->sx, sp->ev_y[y_ready], 0));
             }
+            if (y_ready == 0 && G > 1) { SLAB_TRY(slab_wait(sp, sp->w_ready(0), 1, sp->epoch, sp->sx)); sp->mark("peers_ready", -1, -1, sp->sx); }
+        }
+        // rows {z in chunk k} x {y in chunk c}: row (z, y) starts at slab[(z*Y + y)*X]; its x-block h goes to
+        // xslab_h[(y*Z + rank*Zl + z)*Xb]
+        char* src = zk + (size_t)c * sp->Yc * sp->X * esz;
+        for (int h = 0; h < G; ++h)
+            blk[h] = sp->xslab[h] + ((size_t)c * sp->Yc * sp->Z + (size_t)sp->rank * sp->Zl + (size_t)k * sp->Zk) * sp->Xb * esz;
+        SLAB_TRY(b2fft_plan_set_output_blocks(xp, G, blk.data(), nullptr, 1, sp->Z * sp->Xb));
+        SLAB_TRY(b2fft_plan_set_outer_split(xp, sp->Yc, sp->X, sp->Y * sp->X, sp->Z * sp->Xb, sp->Xb));
+        SLAB_TRY(b2fft_execute(xp, src, nullptr, src, nullptr, 0, 1, sp->sx));
+        sp->mark(whole ? "Xall" : "X", whole ? c : k, whole ? -1 : c, sp->sx);
+        if ((done_in_column[c] += whole ? K : 1) == K) {
+            if (G > 1) {
+                SLAB_TRY(slab_signal(sp, sp->w_chunk(sp->rank, c), sp->sx));
+                SLAB_TRY(slab_wait(sp, sp->w_chunk(0, c), C, sp->epoch, sp->sz));
+                sp->mark("chunk_arrived", c, -1, sp->sz);
+            } else {
+                SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
+                SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_sx, 0));
+            }
+            char* zc = sp->xslab[sp->rank] + (size_t)c * sp->Yc * sp->Z * sp->Xb * esz;
+            SLAB_TRY(b2fft_execute(sp->fwd_z, zc, nullptr, zc, nullptr, 0, 1, sp->sz));
+            sp->mark("Z", c, -1, sp->sz);
         }
     }
     SLAB_CUDA(cudaEventRecord(sp->ev_sx, sp->sx));
@@ -500,6 +550,7 @@ int64_t b2fft_slab_plan_launch_count(const b2fft_slab_plan* sp) {
     for (auto* p : subs)
         if (p) n += b2fft_plan_launch_count(p);
     if (sp->fwd_y_all) n += b2fft_plan_launch_count(sp->fwd_y_all);
+    if (sp->fwd_x_all) n += b2fft_plan_launch_count(sp->fwd_x_all);
     return n;
 }
 
@@ -527,6 +578,7 @@ int b2fft_slab_plan_destroy(b2fft_slab_plan* sp) {
     for (auto* p : subs)
         if (p) b2fft_plan_destroy(p);
     if (sp->fwd_y_all) b2fft_plan_destroy(sp->fwd_y_all);
+    if (sp->fwd_x_all) b2fft_plan_destroy(sp->fwd_x_all);
     if (sp->ws_y_all) cudaFree(sp->ws_y_all);
     if (sp->d_progress) cudaFree(sp->d_progress);
     for (void* w : sp->ws)

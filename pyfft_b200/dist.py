@@ -150,7 +150,7 @@ class SlabPlan(object):
 
     def __init__(self, shape, dtype=numpy.complex64, group=None, normalize=True, scale=1.0, fast_math=True,
                  exchange="xslab", device=None, yslab_layout="zyx", chunks=1, exchange_ctas_per_sm=3, z_chunks=0,
-                 overlap_sms=None):
+                 overlap_sms=None, overlap_columns=0):
         import torch
         import torch.distributed as dist
         if len(shape) != 3:
@@ -170,6 +170,7 @@ class SlabPlan(object):
         # possible, else 1); overlap_sms: SMs left to the exchange while the Y pass runs (None = default, 0 = off)
         self.z_chunks = max(0, int(z_chunks))
         self.overlap_sms = overlap_sms
+        self.overlap_columns = int(overlap_columns)
         self._normalize, self._scale, self._fast_math = bool(normalize), float(scale), bool(fast_math)
         self._native = None
         self._torch, self._dist = torch, dist
@@ -276,6 +277,8 @@ class SlabPlan(object):
             rc = lib.b2fft_slab_plan_set_overlap(h, int(self.overlap_sms))
             if rc not in (_lib.OK, _lib.E_UNSUPPORTED):
                 self._check(rc)
+        if self.overlap_columns:
+            self._check(lib.b2fft_slab_plan_set_option(h, b"overlap_columns", float(self.overlap_columns)))
         geo = (ctypes.c_int64 * 8)()
         self._check(lib.b2fft_slab_plan_geometry(h, geo))
         self.chunks, self.z_chunks = int(geo[2]), int(geo[3])

@@ -65,6 +65,33 @@ def test_xslab_plan_single_rank(cuda_device, shape, dtype, chunks, z_chunks):
     plan.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(64, 64, 2048), (16, 128, 4096), (128, 128, 128)])
+def test_xslab_blocked_store_modes(cuda_device, shape, mode):
+    """The three ways the exchange pass stores its destination-blocked lines (b2fft_set_option "blk_bulk": warp stores,
+    bulk copies staged in the exchange buffer, bulk copies from their own staging buffer that drain while the CTA goes
+    on) give the same x-slabs, bit for bit."""
+    import torch
+    from pyfft_b200 import _lib
+    from pyfft_b200.dist import SlabPlan
+    lib = _lib.load()
+    x = no.make_input(shape, 1, np.complex64, seed=39)[0]
+    outs = []
+    try:
+        for m in (1, mode):
+            _lib.check(lib.b2fft_set_option(b"blk_bulk", float(m)))
+            plan = SlabPlan(shape, dtype=np.complex64, exchange="xslab", chunks=4, z_chunks=2)
+            plan.slab.copy_(torch.from_numpy(x).to(cuda_device))
+            outs.append(plan.forward().clone())
+            torch.cuda.synchronize()
+            plan.close()
+    finally:
+        _lib.check(lib.b2fft_set_option(b"blk_bulk", 1.0))
+    want = np.fft.fftn(x.astype(np.complex128))
+    assert no.rel_l2(outs[1].cpu().numpy().transpose(1, 0, 2), want) < no.tolerance(np.complex64, int(np.prod(shape)))
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_xslab_plan_hidden_y_pass_single_rank(cuda_device):
     """Overlap mode of the native slab plan (b2fft_slab_plan_set_overlap): the Y pass of a 2048-long axis is ONE persistent
     launch (streamed fused two-step kernel) on all but 40 SMs that publishes a progress counter per z-chunk; the X

@@ -54,19 +54,22 @@ def main():
             yzx = ex.endswith("-yzx")
             chunks = int(ex.split("x")[1]) if ex.startswith("ncclx") else 1          # "ncclx8" = 8 pipelined chunks
             xs = ex.startswith("xslab")               # "xslab[xC][zK][cN]": C y-chunks, K z-chunks, N exchange CTAs per SM
-            ctas, zch, ovl = 3, 0, None
+            ctas, zch, ovl, ocol = 3, 0, None, 0
             if xs:       # "xslab[xC][zK][cN][oR]": ... R SMs left to the exchange while the Y pass runs (o0 = Y pass not hidden)
                 import re
-                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?(?:o(\d+))?$", ex)
+                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?(?:o(\d+))?(?:p(\d+))?(?:b(\d))?$", ex)
                 if not m:
                     raise SystemExit("bad exchange spec " + ex)
                 chunks = int(m.group(1)) if m.group(1) else 8
                 zch = int(m.group(2)) if m.group(2) else 0
                 ctas = int(m.group(3)) if m.group(3) else 3
                 ovl = int(m.group(4)) if m.group(4) else None
+                ocol = int(m.group(5)) if m.group(5) else 0          # pN: N y-chunks sent z-chunk by z-chunk beside the Y launch
+                from pyfft_b200 import _lib as _l                    # bM: blocked-store mode (b2fft_set_option "blk_bulk")
+                _l.check(_l.load().b2fft_set_option(b"blk_bulk", float(m.group(6)) if m.group(6) else 1.0))
             plan = SlabPlan(shape, dtype=npdt, exchange="xslab" if xs else "nccl" if ex.startswith("nccl") else ex.split("-")[0],
                             yslab_layout="yzx" if yzx else "zyx", chunks=chunks, exchange_ctas_per_sm=ctas, z_chunks=zch,
-                            overlap_sms=ovl)
+                            overlap_sms=ovl, overlap_columns=ocol)
             L = plan.L
             g = torch.Generator(device=dev)
             g.manual_seed(4242 + rank)
