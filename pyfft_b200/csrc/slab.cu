@@ -109,6 +109,8 @@ struct b2fft_slab_plan {
     b2fft_plan* fwd_y_all = nullptr;
     b2fft_plan* fwd_x_all = nullptr;      // X pass of {all local z} x {one y-chunk}: the columns sent after the Y pass has finished
     int exchange_ctas_per_sm = 0;
+    b2fft_plan* fwd_x_p1 = nullptr;       // X pass of {one z-chunk} x {the first p1_cols y-chunks}: sent while the Y launch runs
+    int p1_cols = 0;
     int overlap_columns = 0;              // y-chunks sent z-chunk by z-chunk while the Y launch runs (0 = default, 3/8 of them)
     void* ws_y_all = nullptr;
     unsigned* d_progress = nullptr;
@@ -412,18 +414,33 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     // Hidden Y pass: the first C1 columns k-major while the Y launch works its way through the z-chunks (they take about as
     // long as the Y pass, so the cells rarely wait), then the other columns one after the other, each as one launch over
     // all z, so that the Z passes start early, spread out and hide under the stores of the following columns.
-    std::vector<std::pair<int, int>> cells;                      // k = -1: all z-chunks of the column in one launch
+    // a cell = one launch: (k, c) rows {z in chunk k} x {y in chunk c}; (k, -n) rows {z in chunk k} x {y in chunks 0..n-1};
+    // (-1, c) rows {all local z} x {y in chunk c}
+    std::vector<std::pair<int, int>> cells;
     // the z-chunk-major part has to last about as long as the Y launch (4.5 of the 13 ms of X work at 2048^3 on 8 GPUs): 3/8
     const int C1 = !overlap ? C : sp->overlap_columns > 0 ? (sp->overlap_columns < C ? sp->overlap_columns : C) : (3 * C + 7) / 8;
-    for (int k = 0; k < K; ++k)
-        for (int c = 0; c < C1; ++c) cells.emplace_back(k, c);
-    for (int c = C1; c < C; ++c) cells.emplace_back(-1, c);
+    if (overlap && (!sp->fwd_x_p1 || sp->p1_cols != C1)) {
+        if (sp->fwd_x_p1) { b2fft_plan_destroy(sp->fwd_x_p1); sp->fwd_x_p1 = nullptr; }
+        const int64_t d[3] = {sp->X, (int64_t)C1 * sp->Yc, sp->Zk};
+        const double nsize = (double)sp->X * (double)sp->Y * (double)sp->Z;
+        SLAB_TRY(b2fft_plan_create_ex(&sp->fwd_x_p1, d, B2FFT_AXIS_X, sp->prec, B2FFT_INTERLEAVED, sp->normalize, sp->scale, sp->fast_math,
+                                      sp->device, nsize, 0));
+        if (sp->exchange_ctas_per_sm > 0) SLAB_TRY(b2fft_plan_set_exchange_ctas(sp->fwd_x_p1, sp->exchange_ctas_per_sm));
+        sp->p1_cols = C1;
+    }
+    if (overlap) {
+        for (int k = 0; k < K; ++k) cells.emplace_back(k, -C1);
+        for (int c = C1; c < C; ++c) cells.emplace_back(-1, c);
+    } else {
+        for (int k = 0; k < K; ++k)
+            for (int c = 0; c < C; ++c) cells.emplace_back(k, c);
+    }
     std::vector<int> done_in_column(C, 0);
     int y_ready = -1;                                            // z-chunks whose Y pass the exchange stream has waited for
     for (const auto& cell : cells) {
-        const bool whole = cell.first < 0;
-        const int k = whole ? 0 : cell.first, c = cell.second;
-        b2fft_plan* xp = whole ? sp->fwd_x_all : sp->fwd_x;
+        const bool whole = cell.first < 0, multi = cell.second < 0;
+        const int k = whole ? 0 : cell.first, c = multi ? 0 : cell.second, ncols = multi ? -cell.second : 1;
+        b2fft_plan* xp = whole ? sp->fwd_x_all : multi ? sp->fwd_x_p1 : sp->fwd_x;
         char* zk = sp->slab + (size_t)k * sp->Zk * sp->Y * sp->X * esz;
         while (y_ready < (whole ? K - 1 : k)) {
             ++y_ready;
@@ -446,10 +463,12 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
         for (int h = 0; h < G; ++h)
             blk[h] = sp->xslab[h] + ((size_t)c * sp->Yc * sp->Z + (size_t)sp->rank * sp->Zl + (size_t)k * sp->Zk) * sp->Xb * esz;
         SLAB_TRY(b2fft_plan_set_output_blocks(xp, G, blk.data(), nullptr, 1, sp->Z * sp->Xb));
-        SLAB_TRY(b2fft_plan_set_outer_split(xp, sp->Yc, sp->X, sp->Y * sp->X, sp->Z * sp->Xb, sp->Xb));
+        SLAB_TRY(b2fft_plan_set_outer_split(xp, (int64_t)ncols * sp->Yc, sp->X, sp->Y * sp->X, sp->Z * sp->Xb, sp->Xb));
         SLAB_TRY(b2fft_execute(xp, src, nullptr, src, nullptr, 0, 1, sp->sx));
-        sp->mark(whole ? "Xall" : "X", whole ? c : k, whole ? -1 : c, sp->sx);
-        if ((done_in_column[c] += whole ? K : 1) == K) {
+        sp->mark(whole ? "Xall" : multi ? "Xcols" : "X", whole ? c : k, whole || multi ? -1 : c, sp->sx);
+        for (int cc = c; cc < c + ncols; ++cc) {
+            if ((done_in_column[cc] += whole ? K : 1) != K) continue;
+            const int c = cc;
             if (G > 1) {
                 SLAB_TRY(slab_signal(sp, sp->w_chunk(sp->rank, c), sp->sx));
                 SLAB_TRY(slab_wait(sp, sp->w_chunk(0, c), C, sp->epoch, sp->sz));
@@ -551,6 +570,7 @@ int64_t b2fft_slab_plan_launch_count(const b2fft_slab_plan* sp) {
         if (p) n += b2fft_plan_launch_count(p);
     if (sp->fwd_y_all) n += b2fft_plan_launch_count(sp->fwd_y_all);
     if (sp->fwd_x_all) n += b2fft_plan_launch_count(sp->fwd_x_all);
+    if (sp->fwd_x_p1) n += b2fft_plan_launch_count(sp->fwd_x_p1);
     return n;
 }
 
@@ -579,6 +599,7 @@ int b2fft_slab_plan_destroy(b2fft_slab_plan* sp) {
         if (p) b2fft_plan_destroy(p);
     if (sp->fwd_y_all) b2fft_plan_destroy(sp->fwd_y_all);
     if (sp->fwd_x_all) b2fft_plan_destroy(sp->fwd_x_all);
+    if (sp->fwd_x_p1) b2fft_plan_destroy(sp->fwd_x_p1);
     if (sp->ws_y_all) cudaFree(sp->ws_y_all);
     if (sp->d_progress) cudaFree(sp->d_progress);
     for (void* w : sp->ws)
