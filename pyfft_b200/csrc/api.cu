@@ -429,6 +429,7 @@ int add_axis(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
     if (lg <= reg.max_log2(pl->prec, contiguous)) return add_pass(pl, axis, n, inner, contiguous, 0, 0);
     const int col = reg.max_log2(pl->prec, false);
     if (col < 1) return fail(B2FFT_E_UNSUPPORTED, "no strided-axis kernels in this build");
+    if (!is_pow2(inner)) return fail(B2FFT_E_UNSUPPORTED, "four-step split of an axis behind a non-power-of-two untransformed axis");
     const int npass = (lg + col - 1) / col;
     const int l1 = lg / npass;
     const long long n1 = 1LL << l1, n2 = n >> l1;
@@ -577,8 +578,12 @@ int b2fft_plan_create_ex(b2fft_plan** out, const int64_t dims_xyz[3], int axes_m
                          int normalize, double scale, int fast_math, int device, double norm_size, int apply_scale) {
     if (!out || !dims_xyz) return fail(B2FFT_E_INVALID, "null argument");
     *out = nullptr;
+    if (axes_mask < 0 || axes_mask > 7) return fail(B2FFT_E_INVALID, "bad axes mask %d", axes_mask);
+    // transformed axes: powers of two (pyfft/plan.py:23-24); an axis the mask leaves out only counts lines and may have any
+    // length (slab pipeline: the X pass over a z-chunk x three of eight y-chunks)
     for (int a = 0; a < 3; ++a)
-        if (!is_pow2(dims_xyz[a])) return fail(B2FFT_E_INVALID, "Array dimensions must be powers of two");
+        if (((axes_mask >> a) & 1) ? !is_pow2(dims_xyz[a]) : dims_xyz[a] < 1)
+            return fail(B2FFT_E_INVALID, "Array dimensions must be powers of two");
     if (precision != B2FFT_F32 && precision != B2FFT_F64) return fail(B2FFT_E_INVALID, "bad precision %d", precision);
     if (layout != B2FFT_INTERLEAVED && layout != B2FFT_SPLIT) return fail(B2FFT_E_INVALID, "bad layout %d", layout);
     if (!(scale == scale) || scale == 0.0) return fail(B2FFT_E_INVALID, "scale must be a non-zero number");

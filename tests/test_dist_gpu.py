@@ -92,7 +92,8 @@ def test_xslab_blocked_store_modes(cuda_device, shape, mode):
     assert torch.equal(outs[0], outs[1])
 
 
-def test_xslab_plan_hidden_y_pass_single_rank(cuda_device):
+@pytest.mark.parametrize("chunks,columns", [(4, 0), (8, 0), (8, 5), (8, 8)])
+def test_xslab_plan_hidden_y_pass_single_rank(cuda_device, chunks, columns):
     """Overlap mode of the native slab plan (b2fft_slab_plan_set_overlap): the Y pass of a 2048-long axis is ONE persistent
     launch (streamed fused two-step kernel) on all but 40 SMs that publishes a progress counter per z-chunk; the X
     passes of z-chunk k wait for counter k on another stream.  Same result as the event-ordered schedule, repeatedly
@@ -100,9 +101,11 @@ def test_xslab_plan_hidden_y_pass_single_rank(cuda_device):
     import torch
     from pyfft_b200.dist import SlabPlan
     shape, dtype = (16, 2048, 64), np.complex64
-    plan = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=4, z_chunks=4, overlap_sms=40)
+    # chunks = 8: the launches that go out beside the Y pass cover 3 (or `columns`) of the 8 y-chunks -- a line count that is
+    # not a power of two
+    plan = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=chunks, z_chunks=4, overlap_sms=40, overlap_columns=columns)
     assert "hidden under the exchange" in plan.describe() and "_fused2p" in plan.describe()
-    ref = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=4, z_chunks=4, overlap_sms=0)
+    ref = SlabPlan(shape, dtype=dtype, exchange="xslab", chunks=chunks, z_chunks=4, overlap_sms=0)
     assert "hidden under the exchange" not in ref.describe()
     x = no.make_input(shape, 1, dtype, seed=29)[0]
     want = np.fft.fftn(x.astype(np.complex128))

@@ -10,7 +10,7 @@ fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29551"
 VARS=${3:-"xslabx8z1o0 xslabx8z8o40 xslabx8z8o56 xslabx8z4o40"}
 echo "== slab 2048 variants ($G ranks)"
-SLAB_TRACE=1 timeout 900 $TR tools/slab_check.py --size 2048 --steps 4 --warmup 2 --exchange $VARS 2>&1 | grep '^{' > $OUT/slab2048_g$G.jsonl
+SLAB_TRACE=1 timeout 900 $TR tools/slab_check.py --size 2048 --steps 4 --warmup 2 --exchange $VARS > $OUT/slab2048_g$G.log 2>&1; grep '^{' $OUT/slab2048_g$G.log > $OUT/slab2048_g$G.jsonl; grep -iE "error|Traceback" $OUT/slab2048_g$G.log | sort | uniq -c | head -5
 python - <<PY
 import json
 for l in open("$OUT/slab2048_g$G.jsonl"):
