@@ -194,7 +194,8 @@ B2FFT_API int b2fft_slab_plan_attach(b2fft_slab_plan* plan, void* slab, void* co
  * these dimensions cannot publish progress.  Call before the first forward. */
 B2FFT_API int b2fft_slab_plan_set_overlap(b2fft_slab_plan* plan, int reserved_sms);
 /* Tuning knobs of the pipeline.  "overlap_columns": how many y-chunks are sent z-chunk by z-chunk while the hidden Y launch
- * is still running (the rest go out one y-chunk at a time over all z); 0 = default (3/8 of the y-chunks). */
+ * is still running (the rest go out one y-chunk at a time over all z); 0 = default (the fraction 0.364*G/(G-1) of the y-chunks,
+ * i.e. as long as the Y launch takes: 3 of 8 on 8 GPUs, 4 of 8 on 4). */
 B2FFT_API int b2fft_slab_plan_set_option(b2fft_slab_plan* plan, const char* key, double value);
 B2FFT_API int b2fft_slab_forward(b2fft_slab_plan* plan, void* cuda_stream);
 B2FFT_API int b2fft_slab_inverse(b2fft_slab_plan* plan, void* cuda_stream);

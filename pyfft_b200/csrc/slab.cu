@@ -180,12 +180,12 @@ int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int
     sp->esz = precision ? 16 : 8;
     sp->normalize = normalize; sp->fast_math = fast_math; sp->scale = scale;
     sp->exchange_ctas_per_sm = G > 1 ? exchange_ctas_per_sm : 0;
-    // default pipeline: 8 y-chunks; 4 z-chunks with the Y pass hidden under the exchange when that is possible and pays
+    // default pipeline: 8 y-chunks; 8 z-chunks with the Y pass hidden under the exchange when that is possible and pays
     // (>= 4 ranks: the exchange, not HBM, bounds the transform), else one z-chunk
     int want_overlap = -1;
     if (const char* e = getenv("B2FFT_SLAB_OVERLAP_SMS")) want_overlap = atoi(e);
     const bool try_overlap = G > 1 && (want_overlap > 0 || (want_overlap < 0 && G >= 4));
-    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : (try_overlap ? 4 : 1);
+    long long C = y_chunks > 0 ? y_chunks : 8, K = z_chunks > 0 ? z_chunks : (try_overlap ? 8 : 1);
     if (C > Y) C = Y;
     while (Y % C) --C;
     if (K > sp->Zl) K = sp->Zl;
@@ -202,7 +202,13 @@ int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int
     // forward: Y pass per z-chunk, X pass per (z-chunk, y-chunk) with blocked stores, Z pass per y-chunk with the scale
     if ((rc = mk(&sp->fwd_y, X, Y, sp->Zk, B2FFT_AXIS_Y, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
     if ((rc = mk(&sp->fwd_x, X, sp->Yc, sp->Zk, B2FFT_AXIS_X, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
-    if ((rc = mk(&sp->fwd_z, sp->Xb, Z, sp->Yc, B2FFT_AXIS_Y, 1)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
+    // the Z pass runs beside the exchange kernels of the following y-chunks: $B2FFT_SLAB_Z_VARIANT names the kernel variant it
+    // should prefer (tuning: a kernel that leaves room for the exchange CTAs on its SMs against the fastest one)
+    const char* zv = getenv("B2FFT_SLAB_Z_VARIANT");
+    if (zv && *zv) b2fft_set_preferred_variants(zv);
+    rc = mk(&sp->fwd_z, sp->Xb, Z, sp->Yc, B2FFT_AXIS_Y, 1);
+    if (zv && *zv) b2fft_set_preferred_variants(getenv("B2FFT_PREFER") ? getenv("B2FFT_PREFER") : "");
+    if (rc != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
     // inverse: Z pass per y-chunk, X pass per y-chunk pulling from the peers, Y pass over the whole slab with the scale
     if ((rc = mk(&sp->inv_z, sp->Xb, Z, sp->Yc, B2FFT_AXIS_Y, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
     if ((rc = mk(&sp->inv_x, X, sp->Yc, sp->Zl, B2FFT_AXIS_X, 0)) != B2FFT_OK) return fail_free(slab_fail(rc, "%s", b2fft_last_error()));
@@ -280,9 +286,9 @@ int b2fft_slab_plan_set_overlap(b2fft_slab_plan* sp, int reserved_sms) {
     }
     int sms = 0;
     SLAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sp->device));
-    // default: the X pass runs 43 GB/s of rows per SM (profiles/r02_slab_pipeline.md), so ~40 SMs carry the 700 GB/s a
-    // GPU can store into its peers
-    int r = reserved_sms > 0 ? reserved_sms : (sms * 40) / 148;
+    // default: 48 of 148 SMs -- measured on 8 B200s at 2048^3 (profiles/r02_slab_pipeline.md): 40 SMs starve the exchange
+    // (15.5-15.7 ms), 56-64 slow the Y and Z passes down (15.2-16.0 ms), 48: 14.9 ms
+    int r = reserved_sms > 0 ? reserved_sms : (sms * 48) / 148;
     if (r < 1) r = 1;
     if (r > sms - 1) r = sms - 1;
     if (!sp->fwd_y_all) {
@@ -417,8 +423,13 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     // a cell = one launch: (k, c) rows {z in chunk k} x {y in chunk c}; (k, -n) rows {z in chunk k} x {y in chunks 0..n-1};
     // (-1, c) rows {all local z} x {y in chunk c}
     std::vector<std::pair<int, int>> cells;
-    // the z-chunk-major part has to last about as long as the Y launch (4.5 of the 13 ms of X work at 2048^3 on 8 GPUs): 3/8
-    const int C1 = !overlap ? C : sp->overlap_columns > 0 ? (sp->overlap_columns < C ? sp->overlap_columns : C) : (3 * C + 7) / 8;
+    // the z-chunk-major part has to last about as long as the Y launch: measured at 2048^3 on B200 the Y launch takes 41.7/G ms
+    // on 100 SMs and the exchange 114.5*(G-1)/G^2 ms at 600 GB/s, i.e. a fraction 0.364*G/(G-1) of the columns (8 GPUs: 3 of 8,
+    // where 2 and 4 of 8 measured 0.6-1.2 ms slower; 4 GPUs: 4 of 8)
+    int c1_default = (int)((double)C * 0.364 * G / (G > 1 ? G - 1 : 1) + 0.5);
+    if (c1_default < 1) c1_default = 1;
+    if (c1_default > C) c1_default = C;
+    const int C1 = !overlap ? C : sp->overlap_columns > 0 ? (sp->overlap_columns < C ? sp->overlap_columns : C) : c1_default;
     if (overlap && (!sp->fwd_x_p1 || sp->p1_cols != C1)) {
         if (sp->fwd_x_p1) { b2fft_plan_destroy(sp->fwd_x_p1); sp->fwd_x_p1 = nullptr; }
         const int64_t d[3] = {sp->X, (int64_t)C1 * sp->Yc, sp->Zk};

@@ -57,7 +57,7 @@ def main():
             ctas, zch, ovl, ocol = 3, 0, None, 0
             if xs:       # "xslab[xC][zK][cN][oR]": ... R SMs left to the exchange while the Y pass runs (o0 = Y pass not hidden)
                 import re
-                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?(?:o(\d+))?(?:p(\d+))?(?:b(\d))?$", ex)
+                m = re.match(r"xslab(?:x(\d+))?(?:z(\d+))?(?:c(\d+))?(?:o(\d+))?(?:p(\d+))?(?:b(\d))?(?:v(\d))?$", ex)
                 if not m:
                     raise SystemExit("bad exchange spec " + ex)
                 chunks = int(m.group(1)) if m.group(1) else 8
@@ -65,6 +65,8 @@ def main():
                 ctas = int(m.group(3)) if m.group(3) else 3
                 ovl = int(m.group(4)) if m.group(4) else None
                 ocol = int(m.group(5)) if m.group(5) else 0          # pN: N y-chunks sent z-chunk by z-chunk beside the Y launch
+                # vN: kernel of the Z pass (1 = TMA-staged W=4 tiles that share their SMs with the exchange CTAs, 0 = default)
+                os.environ["B2FFT_SLAB_Z_VARIANT"] = {"1": "float_n11_w4_g1_b1_r16x16x8x1_tmac1", "2": "float_n11_w4_g1_b1_r16x16x8x1_tmac2"}.get(m.group(7) or "0", "")
                 from pyfft_b200 import _lib as _l                    # bM: blocked-store mode (b2fft_set_option "blk_bulk")
                 _l.check(_l.load().b2fft_set_option(b"blk_bulk", float(m.group(6)) if m.group(6) else 1.0))
             plan = SlabPlan(shape, dtype=npdt, exchange="xslab" if xs else "nccl" if ex.startswith("nccl") else ex.split("-")[0],
