@@ -115,6 +115,7 @@ struct b2fft_slab_plan {
     void* ws_y_all = nullptr;
     unsigned* d_progress = nullptr;
     int overlap_sms = 0;
+    int z_max_ctas = 0;
     unsigned progress_target = 0;
     int normalize = 1, fast_math = 1;
     double scale = 1.0;
@@ -326,7 +327,8 @@ int b2fft_slab_plan_set_overlap(b2fft_slab_plan* sp, int reserved_sms) {
         }
     }
     // the Z passes run beside the exchange of the following columns: they leave it the same SMs
-    if ((rc = b2fft_plan_set_max_ctas(sp->fwd_z, sms - r)) != B2FFT_OK) return slab_fail(rc, "%s", b2fft_last_error());
+    sp->z_max_ctas = sms - r;
+    if ((rc = b2fft_plan_set_max_ctas(sp->fwd_z, sp->z_max_ctas)) != B2FFT_OK) return slab_fail(rc, "%s", b2fft_last_error());
     sp->overlap_sms = r;
     return B2FFT_OK;
 }
@@ -489,7 +491,12 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
                 SLAB_CUDA(cudaStreamWaitEvent(sp->sz, sp->ev_sx, 0));
             }
             char* zc = sp->xslab[sp->rank] + (size_t)c * sp->Yc * sp->Z * sp->Xb * esz;
+            // the Z pass of the column that arrives last has nothing to share the GPU with: no grid cap
+            int z_done = 0;
+            for (int q = 0; q < C; ++q) z_done += done_in_column[q] == K ? 1 : 0;
+            if (overlap && z_done == C) SLAB_TRY(b2fft_plan_set_max_ctas(sp->fwd_z, 0));
             SLAB_TRY(b2fft_execute(sp->fwd_z, zc, nullptr, zc, nullptr, 0, 1, sp->sz));
+            if (overlap && z_done == C) SLAB_TRY(b2fft_plan_set_max_ctas(sp->fwd_z, sp->z_max_ctas));
             sp->mark("Z", c, -1, sp->sz);
         }
     }
