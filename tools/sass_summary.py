@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-COLS = ["FFMA2", "FADD2", "FMUL2", "FFMA", "DFMA", "DADD", "DMUL", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS",
+COLS = ["FFMA2", "FADD2", "FMUL2", "FFMA", "DFMA", "DADD", "DMUL", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "LDG", "STG", "LDS", "STS",
         "SHFL", "BAR", "CCTL", "ST.E.STRONG.SYS", "LD.E.STRONG.SYS", "UCGABAR"]
 
 
@@ -84,8 +84,9 @@ def main():
     with open(args.out, "w") as out:
         out.write("SASS summary of %s (cuobjdump -sass; arch %s; %d kernels)\n" % (os.path.relpath(args.lib, ROOT), ",".join(sorted(arch)) or "?", len(names)))
         out.write("Blackwell-native evidence: packed FP32 math (FFMA2/FADD2/FMUL2), TMA tensor copies (UTMALDG/UTMASTG), TMA bulk copies (UBLKCP),\n"
-                  "mbarrier traffic (SYNCS); SHFL = 0 everywhere (exchanges go through shared memory, DESIGN.md section 3.7); the fused two-step kernels carry\n"
-                  "L2 cache-control instructions (CCTL = discard.L2 / prefetch.L2); slab_signal/wait are the .SYS-scope flag kernels.\n\n")
+                  "mbarrier traffic (SYNCS), asynchronous global->shared copies (LDGSTS: the in-place refill of fused2p_fft_kernel); exchanges go through\n"
+                  "shared memory (SHFL only in the lane-pair tuning variant fused2w_fft_kernel); the fused two-step kernels carry L2 cache-control\n"
+                  "instructions (CCTL = discard.L2 / prefetch.L2); slab_signal/wait are the .SYS-scope flag kernels.\n\n")
         hdr = "%-150s %7s " % ("kernel family (sum over its instantiations)", "instrs") + " ".join("%6s" % k[:6] for k in COLS)
         out.write(hdr + "\n")
         for family, f in fam.items():
