@@ -370,7 +370,7 @@ int add_pass(b2fft_plan* pl, int axis, long long n, long long inner, bool contig
     const KernelVariant& kv = reg.v[vi];
     Pass p{};
     p.variant = vi;
-    p.fallback = kv.kind == 0 ? vi : kv.kind == 1 ? reg.pick_direct_w1(pl->prec, lg) : reg.pick_direct_col(pl->prec, lg, inner, fs);
+    p.fallback = kv.kind == 0 ? vi : (kv.kind == 1 || kv.kind == 4) ? reg.pick_direct_w1(pl->prec, lg) : reg.pick_direct_col(pl->prec, lg, inner, fs);
     if (kv.kind == 3 && fs) return fail(B2FFT_E_UNSUPPORTED, "fused variant picked for a transposing pass");
     if (p.fallback < 0) return fail(B2FFT_E_UNSUPPORTED, "no fallback kernel for axis %c", "xyz"[axis]);
     p.axis = axis;

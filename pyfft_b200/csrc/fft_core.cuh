@@ -19,6 +19,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <cmath>
 #include <type_traits>
 #include <utility>
 
@@ -828,6 +829,76 @@ struct Fused2PRows {
     static_assert(32 % CfgA::W == 0 && (RPW * CfgA::G) % PPI == 0, "whole warp iterations per segment");
     static B2_HD int k_of(int k0, int p) { return k0 + p / CfgA::G; }
     static B2_HD int row(int k0, int sg, int p) { return k_of(k0, p) * CfgB::N + sg * CfgA::G + p % CfgA::G; }   // tile row n
+};
+
+// ------------------------------------------------------------------ short contiguous rows: 16-byte accesses + warp shuffles
+// A row of N = 4 .. 64 complex64 elements is shared by N/2 lanes of one warp; lane l holds positions p = 2l, 2l + 1 (ONE
+// 16-byte load per lane: every warp load covers whole 128-byte lines, where the tile program's 8-byte loads of a 4-thread
+// column touch eight lines per instruction).  Radix-2 DIF over the positions: stage s (half = N >> (s+1) >= 2) pairs
+// position p with p ^ half, i.e. lane l with lane l ^ (half/2), same register -- one shfl.sync.bfly per register instead
+// of a shared-memory round trip; the lane that holds the upper element keeps (lower - upper) * w_{2 half}^(p mod half), the
+// other one the sum.  The last stage pairs the lane's own two registers.  Position p then holds X[brev(p)]: lane l stores
+// X[r] and X[r + N/2], r = brev_{log2N - 1}(l) -- per store instruction the lanes of a row cover one contiguous half row.
+// The twiddles depend on the lane only, so they are set up once per thread (sincospi) and reused for every row it handles.
+template <int LOG2N, bool INV>
+struct ShflRow {
+    using T = float;
+    using C = cpx<T>;
+    static_assert(LOG2N >= 2 && LOG2N <= 6, "N/2 lanes of one warp share a row");
+    static constexpr int N = 1 << LOG2N, LP = N / 2, NST = LOG2N - 1;
+    C tw[NST][2];
+    bool upper[NST];
+    B2_HD void init(int l) {
+        static_for<0, NST>([&](auto sc) {
+            constexpr int s = decltype(sc)::value;
+            constexpr int half = N >> (s + 1);                 // >= 2, partner lane = l ^ (half / 2)
+            upper[s] = (l & (half >> 1)) != 0;
+            for (int b = 0; b < 2; ++b) {
+                const int q = 2 * (l % (half / 2)) + b;       // position inside the lower half of the sub-transform
+                T sn, cs;
+#if defined(__CUDA_ARCH__)
+                sincospif((T)q / (T)half, &sn, &cs);          // w_{2 half}^q = exp(-i pi q / half)
+#else
+                sn = (T)std::sin(3.14159265358979323846 * q / half);
+                cs = (T)std::cos(3.14159265358979323846 * q / half);
+#endif
+                tw[s][b] = cmake<T>(cs, -sn);
+            }
+        });
+    }
+    B2_HD static C sel(bool c, const C& a, const C& b) {
+#if defined(__CUDA_ARCH__)
+        C r; r.v = c ? a.v : b.v; return r;
+#else
+        return c ? a : b;
+#endif
+    }
+    // stage s: o = the partner lane's two registers
+    template <int s>
+    B2_HD void stage(C (&v)[2], const C (&o)[2]) const {
+        for (int b = 0; b < 2; ++b) {
+            const C up = cmul<INV>(csub(o[b], v[b]), tw[s][b]);
+            const C lo = cadd(v[b], o[b]);
+            v[b] = sel(upper[s], up, lo);
+        }
+    }
+    B2_HD static void last(C (&v)[2]) {
+        const C a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+    // output index of register 0 (register 1: + N/2)
+    B2_HD static int out_index(int l) {
+        int r = 0;
+        for (int i = 0; i < NST; ++i) r |= ((l >> i) & 1) << (NST - 1 - i);
+        return r;
+    }
+    B2_HD static void scale(C (&v)[2], T sc, int mode) {
+        if (mode == 1) { v[0] = cscale(v[0], sc); v[1] = cscale(v[1], sc); }
+        else if (mode == 2) {
+            for (int b = 0; b < 2; ++b) { T xr, xi; csplit(v[b], xr, xi); v[b] = cmake<T>(xr / sc, xi / sc); }
+        }
+    }
 };
 
 // ------------------------------------------------------------------ lane-pair FFT (warp-shuffle exchange)

@@ -908,6 +908,85 @@ fused2w_fft_kernel(const __grid_constant__ PassParams<float> pa, const __grid_co
     }
 }
 
+// ------------------------------------------------------------------ short contiguous rows: 16-byte loads + warp-shuffle exchanges
+// N = 4 .. 32 complex64 (interleaved or split): see ShflRow in fft_core.cuh.  256 threads per CTA, N/2 lanes per row, every
+// thread walks rows with a grid stride (its twiddles are set up once).  No shared memory, ~40 registers.
+__device__ __forceinline__ cpx<float> b2_shfl_xor_c(const cpx<float>& a, int mask) {
+#if defined(__CUDA_ARCH__)
+    cpx<float> r;
+    r.v = __shfl_xor_sync(0xffffffffu, a.v, mask);        // one 64-bit register pair = one complex value
+    return r;
+#else
+    (void)mask;
+    return a;
+#endif
+}
+
+template <int LOG2N, bool SPLIT, bool INV>
+__global__ void __launch_bounds__(256)
+row_shfl_kernel(const __grid_constant__ PassParams<float> p) {
+    using R = ShflRow<LOG2N, INV>;
+    using C = cpx<float>;
+    constexpr int N = R::N, LP = R::LP, RPW = 32 / LP;                  // rows per warp and step
+    constexpr int U = 4;                                                // independent rows per thread in flight (latency hiding)
+    const int lane = (int)threadIdx.x & 31, l = lane % LP;
+    R r;
+    r.init(l);
+    const int k0 = R::out_index(l);
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (long long row0 = warp * (RPW * U); row0 < p.n_tiles; row0 += warps * (RPW * U)) {   // warp-uniform: the shuffles need every lane
+        C v[U][2];
+        static_for<0, U>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const long long row = row0 + u * RPW + lane / LP;
+            v[u][0] = cmake<float>(0.f, 0.f); v[u][1] = v[u][0];
+            if (row < p.n_tiles) {
+                if constexpr (SPLIT) {
+                    float2 re, im;
+                    const float2* pr = reinterpret_cast<const float2*>(p.in0 + row * p.outer_stride) + l;
+                    const float2* pi = reinterpret_cast<const float2*>(p.in1 + row * p.outer_stride) + l;
+                    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(re.x), "=f"(re.y) : "l"(pr));
+                    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(im.x), "=f"(im.y) : "l"(pi));
+                    v[u][0] = cmake<float>(re.x, im.x); v[u][1] = cmake<float>(re.y, im.y);
+                } else {
+                    float4 q;
+                    const float4* ps = reinterpret_cast<const float4*>(reinterpret_cast<const vec2<float>*>(p.in0) + row * p.outer_stride) + l;
+                    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(ps));
+                    v[u][0] = cmake<float>(q.x, q.y); v[u][1] = cmake<float>(q.z, q.w);
+                }
+            }
+        });
+        static_for<0, U>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const long long row = row0 + u * RPW + lane / LP;
+            static_for<0, R::NST>([&](auto sc) {
+                constexpr int s = decltype(sc)::value;
+                constexpr int mask = (N >> (s + 1)) >> 1;
+                C o[2];
+                o[0] = b2_shfl_xor_c(v[u][0], mask);
+                o[1] = b2_shfl_xor_c(v[u][1], mask);
+                r.template stage<s>(v[u], o);
+            });
+            R::last(v[u]);
+            R::scale(v[u], p.scale, p.scale_mode);
+            if (row < p.n_tiles) {
+                if constexpr (SPLIT) {
+                    float* orow = p.out0 + row * p.out_outer_stride + k0;
+                    float* irow = p.out1 + row * p.out_outer_stride + k0;
+                    float a, b;
+                    csplit(v[u][0], a, b); orow[0] = a; irow[0] = b;
+                    csplit(v[u][1], a, b); orow[N / 2] = a; irow[N / 2] = b;
+                } else {
+                    vec2<float>* orow = reinterpret_cast<vec2<float>*>(p.out0) + row * p.out_outer_stride + k0;
+                    st_c(orow, v[u][0]);
+                    st_c(orow + N / 2, v[u][1]);
+                }
+            }
+        });
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -919,7 +998,8 @@ struct KernelVariant {
     long long smem_bytes;
     int minb;
     int kind;        // 0 = direct global loads, 1 = persistent + TMA bulk staging (contiguous axis), 2 = persistent + TMA tensor staging (strided axes),
-                     // 3 = fused two-step strided kernel (N = N1*N2 through an L2-resident scratch slot per CTA)
+                     // 3 = fused two-step strided kernel (N = N1*N2 through an L2-resident scratch slot per CTA),
+                     // 4 = short-row kernel (16-byte accesses + warp shuffles; plain contiguous passes only)
     int nbuf;        // ring depth for kind 1
     int blk;         // 1: also compiled with destination-blocked stores (slab exchange passes)
     int fs;          // 1: also compiled as a four-step "A" pass (transposed store + inter-pass twiddle)
@@ -1564,6 +1644,60 @@ struct VariantOpsFused2W {
         return v;
     }
 };
+
+template <int LOG2N>
+struct VariantOpsShfl {
+    static int& sms() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }
+    static cudaError_t prepare() {
+        int dev = 0, n = 0;
+        cudaError_t e;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        sms() = n;
+        return cudaSuccess;
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<float>& p = *static_cast<const PassParams<float>*>(params);
+        if (p.out_blk_log2 >= 0 || p.outer_div > 0 || p.fs_t1 != nullptr || p.inner != 1 || p.progress != nullptr ||
+            (p.in_blk_log2 >= 0 && p.in_blk[0] != nullptr))
+            return cudaErrorNotSupported;
+        if (p.n_tiles <= 0) return cudaSuccess;
+        if (sms() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        constexpr int LP = (1 << LOG2N) / 2;
+        long long ctas = (p.n_tiles * LP + 4 * 256 - 1) / (4 * 256);      // four rows per thread and step
+        const long long cap = (long long)sms() * 32;
+        if (ctas > cap) ctas = cap;
+        const dim3 grid((unsigned)ctas), block(256);
+        if (split) row_shfl_kernel<LOG2N, true, false><<<grid, block, 0, stream>>>(p);
+        else if (inv) row_shfl_kernel<LOG2N, false, true><<<grid, block, 0, stream>>>(p);
+        else row_shfl_kernel<LOG2N, false, false><<<grid, block, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, row_shfl_kernel<LOG2N, false, false>, 256, 0) != cudaSuccess) return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v{};
+        v.name = name;
+        v.prec = 0;
+        v.log2n = LOG2N;
+        v.W = 1; v.G = 512 / (1 << LOG2N); v.E = 2; v.S = 1;
+        for (int s = 0; s < 4; ++s) v.radix[s] = s == 0 ? (1 << LOG2N) : 1;
+        v.threads = 256;
+        v.smem_bytes = 0;
+        v.minb = 1;
+        v.kind = 4;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        return v;
+    }
+};
+
+// B2_VR(log2n): short-row kernel, complex64 / split float32, 16-byte accesses + warp-shuffle exchanges
+#define B2_VR(L) out.push_back(::b2::VariantOpsShfl<L>::make("float_n" #L "_w1_shfl"));
 
 // B2_V(type, log2n, W, G, minblocks, R0, R1, R2, R3)
 #define B2_STR2(x) #x

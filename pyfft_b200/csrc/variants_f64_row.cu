@@ -18,6 +18,7 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #define XS B2_VS
 #define XW B2_VW
 #define XP B2_VP
+#define XR B2_VR
 #include "variants.def"
 #undef X
 #undef XT
@@ -33,5 +34,6 @@ void register_f64_row(std::vector<KernelVariant>& out) {
 #undef XS
 #undef XW
 #undef XP
+#undef XR
 }
 }  // namespace b2

@@ -12,6 +12,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a box without a GPU skips the GPU tests instead of erroring in their fixtures; asking for them
+    explicitly (`-m gpu`) without a device still fails loudly in `cuda_device` -- the CUDA path has no fallback."""
+    markexpr = (config.getoption("-m") or "").strip()
+    if "gpu" in markexpr.replace("not gpu", ""):
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible (run with -m gpu on a B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def built_lib():
     """libb2fft.so, built in-tree if missing (nvcc cross-compiles without a GPU)."""

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <array>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -786,6 +787,70 @@ static void check_fused2p(const char* name) {
     bool ok = e0 < tol && e1 < tol;
     std::printf("%-44s fused two-step (streamed, ks=%d) N=%dx%d  err fwd(oop)=%.2e inv(in place)=%.2e thr=%d %s\n", name, KS, CfgA::N,
                 CfgB::N, e0, e1, CfgA::THREADS, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
+// The short-row kernel (kernels.cuh row_shfl_kernel): the lanes of a row run ShflRow stage by stage, the warp shuffle is
+// replaced by handing every lane the registers of lane ^ mask; loads / stores use the kernel's addressing (positions 2l, 2l+1
+// in, X[brev(l)] and X[brev(l) + N/2] out), interleaved and split, forward and conjugated, with the scale applied.
+template <int LOG2N, bool INV, bool SPLIT>
+static double run_shfl(long long rows, unsigned seed) {
+    using R = ShflRow<LOG2N, INV>;
+    using C = cpx<float>;
+    constexpr int N = R::N, LP = R::LP;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<float> re(rows * N), im(rows * N), ore(rows * N, NAN), oim(rows * N, NAN);
+    for (auto& v : re) v = (float)nd(rng);
+    for (auto& v : im) v = (float)nd(rng);
+    for (long long row = 0; row < rows; ++row) {
+        std::vector<R> th(LP);
+        std::vector<std::array<C, 2>> v(LP), o(LP);
+        for (int l = 0; l < LP; ++l) {
+            th[l].init(l);
+            for (int b = 0; b < 2; ++b) v[l][b] = cmake<float>(re[row * N + 2 * l + b], im[row * N + 2 * l + b]);
+        }
+        static_for<0, R::NST>([&](auto sc) {
+            constexpr int s = decltype(sc)::value;
+            constexpr int mask = (N >> (s + 1)) >> 1;
+            for (int l = 0; l < LP; ++l) o[l] = v[l ^ mask];
+            for (int l = 0; l < LP; ++l) {
+                C a[2] = {v[l][0], v[l][1]}, b[2] = {o[l][0], o[l][1]};
+                th[l].template stage<s>(a, b);
+                v[l] = {a[0], a[1]};
+            }
+        });
+        for (int l = 0; l < LP; ++l) {
+            C a[2] = {v[l][0], v[l][1]};
+            R::last(a);
+            R::scale(a, 0.5f, 1);
+            const int k0 = R::out_index(l);
+            for (int b = 0; b < 2; ++b) { ore[row * N + k0 + b * (N / 2)] = a[b].x; oim[row * N + k0 + b * (N / 2)] = a[b].y; }
+        }
+    }
+    (void)SPLIT;      // the two layouts differ in the kernel's load / store instructions only; the emulation holds (re, im) apart
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long row = 0; row < rows; ++row) {
+        for (int n = 0; n < N; ++n) line[n] = INV ? cld(im[row * N + n], re[row * N + n]) : cld(re[row * N + n], im[row * N + n]);
+        ref_fft(line);
+        for (int n = 0; n < N; ++n) {
+            cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+            want *= 0.5L;
+            double e = (double)std::abs(cld(ore[row * N + n], oim[row * N + n]) - want);
+            if (!(e == e)) e = 1e30;
+            max_err = std::max(max_err, e);
+            max_mag = std::max(max_mag, (double)std::abs(want));
+        }
+    }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <int LOG2N>
+static void check_shfl(const char* name) {
+    double e0 = run_shfl<LOG2N, false, false>(5, 61), e1 = run_shfl<LOG2N, true, false>(3, 62);
+    bool ok = e0 < 2e-6 && e1 < 2e-6;
+    std::printf("%-44s short rows (lane shuffles) N=%d  err fwd=%.2e inv=%.2e %s\n", name, 1 << LOG2N, e0, e1, ok ? "ok" : "FAIL");
     if (!ok) ++g_fail;
 }
 

@@ -79,6 +79,17 @@ def test_layout_and_pitch_aware_variant_choice(built_lib):
     assert "_fused2" not in _preview(built_lib, 8, 8192, 2048)[2]["variant"]
 
 
+def test_short_rows_take_the_shuffle_kernel(built_lib):
+    # complex64 / split float32 rows of 4 .. 32 elements: 16-byte accesses + warp-shuffle exchanges (row_shfl_kernel) ...
+    for n in (4, 8, 16, 32):
+        assert _preview(built_lib, n)[0]["variant"] == "float_n%d_w1_shfl" % (n.bit_length() - 1)
+        assert _preview(built_lib, n, layout=1)[0]["variant"].endswith("_shfl")
+    assert _preview(built_lib, 16, 16, 16)[0]["variant"].endswith("_shfl")        # the X pass of a small 3-D transform
+    # ... not for N = 2 and N >= 64 (the tile program is at the copy bandwidth there), not for double precision
+    assert "_shfl" not in _preview(built_lib, 2)[0]["variant"] and "_shfl" not in _preview(built_lib, 64)[0]["variant"]
+    assert "_shfl" not in _preview(built_lib, 16, prec=1)[0]["variant"]
+
+
 def test_preview_validation(built_lib):
     from pyfft_b200 import _lib
     buf = ctypes.create_string_buffer(64)

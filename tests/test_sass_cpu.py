@@ -1,7 +1,8 @@
 """CPU test: the built library really contains the Blackwell-native instructions DESIGN.md claims
 (cuobjdump -sass on the sm_100a cubins inside libb2fft.so; B200_PROFILING.md "what proves a
 Blackwell-native kernel"): packed FP32 butterflies (FADD2 / FMUL2 / FFMA2), TMA bulk copies (UBLKCP),
-TMA tensor loads / stores (UTMALDG / UTMASTG), mbarrier waits (SYNCS) -- and no cuFFT dependency."""
+TMA tensor loads / stores (UTMALDG / UTMASTG), mbarrier waits (SYNCS), asynchronous global->shared copies (LDGSTS: the
+streamed fused two-step kernel), warp shuffles (SHFL: the short-row kernel) -- and no cuFFT dependency."""
 import re
 import shutil
 import subprocess
@@ -16,9 +17,9 @@ def test_sass_mnemonics_present(built_lib):
         proc = subprocess.Popen([cuobjdump, "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True)
     except OSError:
         pytest.skip("cuobjdump not available")
-    counts = {k: 0 for k in ("FADD2", "FMUL2", "FFMA2", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS")}
+    counts = {k: 0 for k in ("FADD2", "FMUL2", "FFMA2", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "SHFL")}
     archs = set()
-    pat = re.compile(r"\b(FADD2|FMUL2|FFMA2|UBLKCP|UTMALDG|UTMASTG|SYNCS)\b")
+    pat = re.compile(r"\b(FADD2|FMUL2|FFMA2|UBLKCP|UTMALDG|UTMASTG|SYNCS|LDGSTS|SHFL)\b")
     for line in proc.stdout:
         if line.startswith("arch ="):
             archs.add(line.split("=")[1].strip())
