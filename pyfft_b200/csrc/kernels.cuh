@@ -272,6 +272,93 @@ tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
     }
 }
 
+// ------------------------------------------------------------------ persistent TMA-fed kernel for LONG rows: staging slot = exchange buffer
+// Rows of 64-128 KiB (N = 8192 / 16384 complex64, 4096 / 8192 complex128) leave room for one or two CTAs per SM and none for
+// a separate staging ring, so the plain kernel's load / transform / store phases run back to back (0.46-0.56 of the copy
+// bandwidth at one CTA per SM).  Here ONE shared-memory buffer is both: the next group of rows is fetched into it by
+// cp.async.bulk as soon as the LAST exchange of the current group has been read (every thread fences its reads against the
+// async proxy and arrives on the "empty" mbarrier; the elected thread waits for that phase and issues the copy), so the
+// HBM reads of group j+1 run beside the last radix stage and the global stores of group j.
+template <class Cfg>
+struct TmaRowAliasLayout {
+    using T = typename Cfg::T;
+    static constexpr size_t IN_BYTES = (size_t)Cfg::G * Cfg::N * 2 * sizeof(T);
+    static constexpr size_t X_BYTES = (size_t)Cfg::SMEM_BYTES;
+    static constexpr size_t BUF_BYTES = ((IN_BYTES > X_BYTES ? IN_BYTES : X_BYTES) + 127) / 128 * 128;
+    static constexpr size_t BAR_OFF = BUF_BYTES;               // full, empty
+    static constexpr size_t TOTAL = BAR_OFF + 16;
+};
+
+template <class Cfg, bool SPLIT, bool INV, int s, class TH, class F>
+__device__ __forceinline__ void run_stages_hook(TH& th, const PassParams<typename Cfg::T>& p, vec2<typename Cfg::T>* smem,
+                                                F&& after_last_read) {
+    th.template compute<s>(p);
+    if constexpr (s + 1 < Cfg::S) {
+        if constexpr (s > 0) __syncthreads();   // previous exchange fully read before it is overwritten
+        th.template xwrite<s>(smem);
+        __syncthreads();
+        th.template xread<s>(smem);
+        if constexpr (s + 2 == Cfg::S) after_last_read();
+        run_stages_hook<Cfg, SPLIT, INV, s + 1>(th, p, smem, static_cast<F&&>(after_last_read));
+    }
+}
+
+template <class Cfg, bool SPLIT, bool INV, int MINB>
+__global__ void __launch_bounds__(Cfg::THREADS, MINB)
+tile_fft_kernel_tma_row_alias(const __grid_constant__ PassParams<typename Cfg::T> p) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    using L = TmaRowAliasLayout<Cfg>;
+    static_assert(Cfg::W == 1 && Cfg::S >= 2, "contiguous axis, at least one exchange");
+    extern __shared__ __align__(128) unsigned char b2_smem_raw[];
+    T2* buf = reinterpret_cast<T2*>(b2_smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(b2_smem_raw + L::BAR_OFF);
+    uint64_t* empty = full + 1;
+    const int tid = (int)threadIdx.x;
+    const long long n_groups = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+    const long long stride = gridDim.x;
+    auto issue = [&](long long grp) {
+        long long tiles = p.n_tiles - grp * Cfg::G;
+        if (tiles > Cfg::G) tiles = Cfg::G;
+        const long long first = grp * Cfg::G * Cfg::N;
+        if constexpr (SPLIT) {
+            const uint32_t bytes = (uint32_t)(tiles * Cfg::N * sizeof(T));
+            mbar_expect_tx(full, 2 * bytes);
+            bulk_load(b2_smem_raw, p.in0 + first, bytes, full);
+            bulk_load(b2_smem_raw + L::IN_BYTES / 2, p.in1 + first, bytes, full);
+        } else {
+            const uint32_t bytes = (uint32_t)(tiles * Cfg::N * 2 * sizeof(T));
+            mbar_expect_tx(full, bytes);
+            bulk_load(b2_smem_raw, reinterpret_cast<const T2*>(p.in0) + first, bytes, full);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(full, 1);
+        mbar_init(empty, Cfg::THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long grp = blockIdx.x;
+    if (tid == 0 && grp < n_groups) issue(grp);
+    TileThread<Cfg, SPLIT, INV> th;
+    for (unsigned it = 0; grp < n_groups; ++it, grp += stride) {
+        th.setup(tid, grp, p);
+        mbar_wait(full, it & 1);
+        th.load_smem(b2_smem_raw, b2_smem_raw + L::IN_BYTES / 2);
+        __syncthreads();                       // every thread holds its elements: the buffer becomes the exchange buffer
+        run_stages_hook<Cfg, SPLIT, INV, 0>(th, p, buf, [&] {
+            // the last exchange has been read by this thread: hand the buffer back to the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(empty);
+            if (tid == 0 && grp + stride < n_groups) {
+                mbar_wait(empty, it & 1);
+                issue(grp + stride);
+            }
+        });
+        th.store(p);
+    }
+}
+
 // ------------------------------------------------------------------ persistent TMA-staged kernel (strided axes)
 // Same pipeline as the row version, for tiles of W columns of an [outer][N][inner] array: the tile is
 // fetched with cp.async.bulk.tensor (TMA tiled loads, SASS UTMALDG) through a 3-D tensor map
@@ -1167,6 +1254,58 @@ struct VariantOpsTma {
     }
 };
 
+template <class Cfg, int MINB>
+struct VariantOpsTmaRowAlias {
+    using T = typename Cfg::T;
+    using L = TmaRowAliasLayout<Cfg>;
+    static int& slots() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }
+    static cudaError_t prepare() {
+        const int b = (int)L::TOTAL;
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(tile_fft_kernel_tma_row_alias<Cfg, false, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tile_fft_kernel_tma_row_alias<Cfg, false, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tile_fft_kernel_tma_row_alias<Cfg, true, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_fft_kernel_tma_row_alias<Cfg, false, false, MINB>, Cfg::THREADS, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        slots() = sms * (occ > 0 ? occ : 1);
+        return cudaSuccess;
+    }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+        if (p.out_blk_log2 >= 0 || p.outer_div > 0 || p.fs_t1 != nullptr || p.progress != nullptr ||
+            (p.in_blk_log2 >= 0 && p.in_blk[0] != nullptr))
+            return cudaErrorNotSupported;
+        long long ctas = (p.n_tiles + Cfg::G - 1) / Cfg::G;
+        if (ctas <= 0) return cudaSuccess;
+        if (slots() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        if (ctas > slots()) ctas = slots();
+        const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
+        const size_t sm = L::TOTAL;
+        if (split) tile_fft_kernel_tma_row_alias<Cfg, true, false, MINB><<<grid, block, sm, stream>>>(p);
+        else if (inv) tile_fft_kernel_tma_row_alias<Cfg, false, true, MINB><<<grid, block, sm, stream>>>(p);
+        else tile_fft_kernel_tma_row_alias<Cfg, false, false, MINB><<<grid, block, sm, stream>>>(p);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_fft_kernel_tma_row_alias<Cfg, false, false, MINB>, Cfg::THREADS, L::TOTAL) != cudaSuccess) return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v = VariantOps<Cfg, MINB, false>::make(name);
+        v.smem_bytes = (long long)L::TOTAL;
+        v.kind = 1;
+        v.nbuf = 0;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        return v;
+    }
+};
+
 // ---- host side of the tensor-map variants
 typedef CUresult (*b2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1720,6 +1859,11 @@ struct VariantOpsShfl {
 #define B2_VT(T, L, G, MB, NB, R0, R1, R2, R3)                                                       \
     out.push_back(::b2::VariantOpsTma<::b2::TileCfg<T, L, 1, G, R0, R1, R2, R3>, MB, NB>::make(        \
         #T "_n" B2_STR(L) "_w1_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tma" B2_STR(NB)));
+
+// B2_VTA(type, log2n, G, minblocks, R0..R3): persistent TMA-staged contiguous-axis variant whose staging slot is the exchange buffer
+#define B2_VTA(T, L, G, MB, R0, R1, R2, R3)                                                          \
+    out.push_back(::b2::VariantOpsTmaRowAlias<::b2::TileCfg<T, L, 1, G, R0, R1, R2, R3>, MB>::make(    \
+        #T "_n" B2_STR(L) "_w1_g" B2_STR(G) "_b" B2_STR(MB) "_r" B2_STR(R0) "x" B2_STR(R1) "x" B2_STR(R2) "x" B2_STR(R3) "_tmara"));
 
 // B2_VC(type, log2n, W, G, minblocks, ring depth, R0..R3): persistent TMA tensor-staged strided-axis variant
 #define B2_VC(T, L, W, G, MB, NB, R0, R1, R2, R3)                                                    \

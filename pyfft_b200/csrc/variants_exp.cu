@@ -19,6 +19,7 @@ void register_exp(std::vector<KernelVariant>& out) {
 #define XW B2_VW
 #define XP B2_VP
 #define XR B2_VR
+#define XTA B2_VTA
 #include "variants.def"
 #undef X
 #undef XT
@@ -35,5 +36,6 @@ void register_exp(std::vector<KernelVariant>& out) {
 #undef XW
 #undef XP
 #undef XR
+#undef XTA
 }
 }  // namespace b2

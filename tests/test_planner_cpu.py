@@ -90,6 +90,16 @@ def test_short_rows_take_the_shuffle_kernel(built_lib):
     assert "_shfl" not in _preview(built_lib, 16, prec=1)[0]["variant"]
 
 
+def test_long_rows_take_the_aliased_tma_kernel(built_lib):
+    # rows of 64-128 KiB: persistent TMA-staged kernel whose staging slot is the exchange buffer (tile_fft_kernel_tma_row_alias)
+    assert _preview(built_lib, 16384)[0]["variant"].endswith("_tmara")
+    assert _preview(built_lib, 8192)[0]["variant"].endswith("_tmara")
+    assert _preview(built_lib, 8192, prec=1)[0]["variant"].endswith("_tmara")
+    assert _preview(built_lib, 16384, layout=1)[0]["variant"].endswith("_tmara")
+    # ... complex128 4096 keeps the plain kernel (two CTAs per SM, 0.95 of the copy bandwidth)
+    assert "_tma" not in _preview(built_lib, 4096, prec=1)[0]["variant"]
+
+
 def test_preview_validation(built_lib):
     from pyfft_b200 import _lib
     buf = ctypes.create_string_buffer(64)
