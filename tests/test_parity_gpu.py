@@ -49,7 +49,7 @@ def _run(plan, dev, data, batch, inverse, inplace):
 
 # reference grid: 1D 2^{3,8,9,10,11,13}, 2D {2^4,2^7,2^8,2^10}^2, 3D {2^4,2^7}^3 (the 2^10 3D cases and
 # 1D 2^20 need the multi-pass path and are covered in test_large.py when present), capped at 32 MB
-SHAPES_1D = [(1 << k,) for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13)]
+SHAPES_1D = [(1 << k,) for k in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14)]     # 2^14: the longest single-pass complex64 row
 SHAPES_2D = [(1 << a, 1 << b) for a in (4, 7, 8, 10) for b in (4, 7, 8, 10)]
 SHAPES_3D = [(1 << a, 1 << b, 1 << c) for a in (4, 7) for b in (4, 7) for c in (4, 7)] + [(2, 2, 2), (4, 8, 2), (256, 4, 64)]
 BATCHES = [1, 16, 128, 1024, 4096]      # test/test_errors.py:139
