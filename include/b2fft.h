@@ -181,6 +181,11 @@ typedef struct b2fft_slab_plan b2fft_slab_plan;
 B2FFT_API int b2fft_slab_plan_create(b2fft_slab_plan** out, const int64_t dims_xyz[3], int precision, int normalize,
                                      double scale, int fast_math, int device, int rank, int nranks, int y_chunks,
                                      int z_chunks, int exchange_ctas_per_sm);
+/* The order of the X-pass launches b2fft_slab_forward would issue for this pipeline shape, without touching a device:
+ * "k:c;" = rows {z in chunk k} x {y in chunk c}, "k:0-n;" = {z in chunk k} x {y-chunks 0..n}, "all:c;" = {all local z} x
+ * {y in chunk c}.  hidden_y = the Y pass runs as one launch with progress counters (b2fft_slab_plan_set_overlap);
+ * overlap_columns = 0 picks the default for `nranks`. */
+B2FFT_API int b2fft_slab_schedule_preview(int nranks, int y_chunks, int z_chunks, int hidden_y, int overlap_columns, char* buf, size_t buflen);
 B2FFT_API int b2fft_slab_plan_sizes(const b2fft_slab_plan* plan, size_t* slab_bytes, size_t* xslab_bytes, size_t* flag_bytes);
 /* {Z/G, X/G, y_chunks, z_chunks, Y/y_chunks, (Z/G)/z_chunks, G, rank} */
 B2FFT_API int b2fft_slab_plan_geometry(const b2fft_slab_plan* plan, int64_t out[8]);

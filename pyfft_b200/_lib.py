@@ -52,6 +52,7 @@ SIGNATURES = {
     "b2fft_plan_set_progress": (_i, [_vp, _vp, _i64, _i, ctypes.POINTER(_i64)]),
     "b2fft_slab_plan_set_overlap": (_i, [_vp, _i]),
     "b2fft_slab_plan_set_option": (_i, [_vp, ctypes.c_char_p, _d]),
+    "b2fft_slab_schedule_preview": (_i, [_i, _i, _i, _i, _i, ctypes.c_char_p, _sz]),
     "b2fft_mem_alloc": (_i, [_sz, _i, ctypes.POINTER(_vp)]),
     "b2fft_mem_free": (_i, [_vp]),
     "b2fft_ipc_export": (_i, [_vp, ctypes.c_char_p]),

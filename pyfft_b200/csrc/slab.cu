@@ -99,6 +99,29 @@ struct DevGuard {
 
 }  // namespace
 
+// ---- the order of the X-pass launches (pure host logic, also exported as b2fft_slab_schedule_preview for the CPU tests)
+// A cell = one launch of the X pass: (k, c) rows {z in chunk k} x {y in chunk c}; (k, -n) rows {z in chunk k} x {y in chunks
+// 0..n-1}; (-1, c) rows {all local z} x {y in chunk c}.
+static int slab_default_columns(int G, int C) {
+    // the z-chunk-major part has to last about as long as the Y launch: measured at 2048^3 on B200 the Y launch takes 41.7/G ms
+    // on 100 SMs and the exchange 114.5*(G-1)/G^2 ms at 600 GB/s, i.e. a fraction 0.364*G/(G-1) of the columns (8 GPUs: 3 of 8,
+    // where 2 and 4 of 8 measured 0.6-1.2 ms slower; 4 GPUs: 4 of 8)
+    int c1 = (int)((double)C * 0.364 * G / (G > 1 ? G - 1 : 1) + 0.5);
+    if (c1 < 1) c1 = 1;
+    if (c1 > C) c1 = C;
+    return c1;
+}
+static void slab_schedule(int K, int C, int C1, bool overlap, std::vector<std::pair<int, int>>& cells) {
+    cells.clear();
+    if (overlap) {
+        for (int k = 0; k < K; ++k) cells.emplace_back(k, -C1);
+        for (int c = C1; c < C; ++c) cells.emplace_back(-1, c);
+    } else {
+        for (int k = 0; k < K; ++k)
+            for (int c = 0; c < C; ++c) cells.emplace_back(k, c);
+    }
+}
+
 struct b2fft_slab_plan {
     long long X, Y, Z, Zl, Xb, Yc, Zk;
     int G, rank, device, prec, C, K;
@@ -343,6 +366,26 @@ int b2fft_slab_plan_set_option(b2fft_slab_plan* sp, const char* key, double valu
     return slab_fail(B2FFT_E_INVALID, "unknown slab option %s", key);
 }
 
+int b2fft_slab_schedule_preview(int nranks, int y_chunks, int z_chunks, int hidden_y, int overlap_columns, char* buf, size_t buflen) {
+    if (!buf || !buflen || nranks < 1 || y_chunks < 1 || z_chunks < 1 || overlap_columns < 0)
+        return slab_fail(B2FFT_E_INVALID, "bad argument");
+    const int C1 = !hidden_y ? y_chunks : overlap_columns > 0 ? (overlap_columns < y_chunks ? overlap_columns : y_chunks)
+                                                                : slab_default_columns(nranks, y_chunks);
+    std::vector<std::pair<int, int>> cells;
+    slab_schedule(z_chunks, y_chunks, C1, hidden_y != 0, cells);
+    std::string out;
+    for (const auto& c : cells) {
+        char item[48];
+        if (c.first < 0) snprintf(item, sizeof item, "all:%d;", c.second);
+        else if (c.second < 0) snprintf(item, sizeof item, "%d:0-%d;", c.first, -c.second - 1);
+        else snprintf(item, sizeof item, "%d:%d;", c.first, c.second);
+        out += item;
+    }
+    if (out.size() + 1 > buflen) return slab_fail(B2FFT_E_INVALID, "buffer too small");
+    snprintf(buf, buflen, "%s", out.c_str());
+    return B2FFT_OK;
+}
+
 int b2fft_slab_plan_sizes(const b2fft_slab_plan* sp, size_t* slab_bytes, size_t* xslab_bytes, size_t* flag_bytes) {
     if (!sp) return slab_fail(B2FFT_E_INVALID, "null plan");
     if (slab_bytes) *slab_bytes = (size_t)(sp->Zl * sp->Y * sp->X) * sp->esz;
@@ -425,13 +468,7 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
     // a cell = one launch: (k, c) rows {z in chunk k} x {y in chunk c}; (k, -n) rows {z in chunk k} x {y in chunks 0..n-1};
     // (-1, c) rows {all local z} x {y in chunk c}
     std::vector<std::pair<int, int>> cells;
-    // the z-chunk-major part has to last about as long as the Y launch: measured at 2048^3 on B200 the Y launch takes 41.7/G ms
-    // on 100 SMs and the exchange 114.5*(G-1)/G^2 ms at 600 GB/s, i.e. a fraction 0.364*G/(G-1) of the columns (8 GPUs: 3 of 8,
-    // where 2 and 4 of 8 measured 0.6-1.2 ms slower; 4 GPUs: 4 of 8)
-    int c1_default = (int)((double)C * 0.364 * G / (G > 1 ? G - 1 : 1) + 0.5);
-    if (c1_default < 1) c1_default = 1;
-    if (c1_default > C) c1_default = C;
-    const int C1 = !overlap ? C : sp->overlap_columns > 0 ? (sp->overlap_columns < C ? sp->overlap_columns : C) : c1_default;
+    const int C1 = !overlap ? C : sp->overlap_columns > 0 ? (sp->overlap_columns < C ? sp->overlap_columns : C) : slab_default_columns(G, C);
     if (overlap && (!sp->fwd_x_p1 || sp->p1_cols != C1)) {
         if (sp->fwd_x_p1) { b2fft_plan_destroy(sp->fwd_x_p1); sp->fwd_x_p1 = nullptr; }
         const int64_t d[3] = {sp->X, (int64_t)C1 * sp->Yc, sp->Zk};
@@ -441,13 +478,7 @@ int b2fft_slab_forward(b2fft_slab_plan* sp, void* cuda_stream) {
         if (sp->exchange_ctas_per_sm > 0) SLAB_TRY(b2fft_plan_set_exchange_ctas(sp->fwd_x_p1, sp->exchange_ctas_per_sm));
         sp->p1_cols = C1;
     }
-    if (overlap) {
-        for (int k = 0; k < K; ++k) cells.emplace_back(k, -C1);
-        for (int c = C1; c < C; ++c) cells.emplace_back(-1, c);
-    } else {
-        for (int k = 0; k < K; ++k)
-            for (int c = 0; c < C; ++c) cells.emplace_back(k, c);
-    }
+    slab_schedule(K, C, C1, overlap, cells);
     std::vector<int> done_in_column(C, 0);
     int y_ready = -1;                                            // z-chunks whose Y pass the exchange stream has waited for
     for (const auto& cell : cells) {

@@ -350,6 +350,102 @@ static void check_staged(const char* name, long long outer) {
     if (!ok) ++g_fail;
 }
 
+// The long-row kernel (kernels.cuh tile_fft_kernel_tma_row_alias): ONE buffer is staging slot and exchange buffer.  One CTA
+// walks the rows in the kernel's order of events: stage-0 input is read from the buffer; every exchange poisons and rewrites
+// it; right after the LAST exchange has been read the buffer is poisoned and refilled with the next group of rows (what the
+// bulk copy does once every thread has arrived on the "empty" barrier), and only then the last radix stage and the stores
+// of the current rows run -- so a stage that still needed the buffer after the hand-back, or a refill landing in the wrong
+// place, shows up as a wrong result.
+template <class Cfg, bool SPLIT, bool INV, int s, class TH, class F>
+static void emu_stages_hook(std::vector<TH>& th, const PassParams<typename Cfg::T>& p, vec2<typename Cfg::T>* smem, size_t smem_elems,
+                            F&& after_last_read) {
+    for (auto& t : th) t.template compute<s>(p);
+    if constexpr (s + 1 < Cfg::S) {
+        for (size_t i = 0; i < smem_elems; ++i) { smem[i].x = NAN; smem[i].y = NAN; }
+        for (auto& t : th) t.template xwrite<s>(smem);
+        for (auto& t : th) t.template xread<s>(smem);
+        if constexpr (s + 2 == Cfg::S) after_last_read();
+        emu_stages_hook<Cfg, SPLIT, INV, s + 1>(th, p, smem, smem_elems, static_cast<F&&>(after_last_read));
+    }
+}
+
+template <class Cfg, bool SPLIT, bool INV>
+static double run_alias_row(long long rows, unsigned seed) {
+    using T = typename Cfg::T;
+    using T2 = vec2<T>;
+    constexpr int N = Cfg::N, G = Cfg::G;
+    static_assert(Cfg::W == 1 && Cfg::S >= 2, "long contiguous rows");
+    const long long total = rows * N;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<T> in_re(total), in_im(total), out_re(total, (T)NAN), out_im(total, (T)NAN);
+    for (long long i = 0; i < total; ++i) { in_re[i] = (T)nd(rng); in_im[i] = (T)nd(rng); }
+    std::vector<T2> in_c(total), out_c(total);
+    for (long long i = 0; i < total; ++i) { in_c[i].x = in_re[i]; in_c[i].y = in_im[i]; out_c[i].x = NAN; out_c[i].y = NAN; }
+    PassParams<T> p{};
+    std::vector<std::vector<T2>> tabs;
+    for (int s = 0; s + 1 < Cfg::S; ++s) tabs.push_back(make_stage_table<T>(Cfg::NS(s), Cfg::R(s)));
+    for (int s = 0; s + 1 < Cfg::S; ++s) p.tw[s] = reinterpret_cast<const T*>(tabs[s].data());
+    if (SPLIT) { p.in0 = in_re.data(); p.in1 = in_im.data(); p.out0 = out_re.data(); p.out1 = out_im.data(); }
+    else { p.in0 = reinterpret_cast<const T*>(in_c.data()); p.out0 = reinterpret_cast<T*>(out_c.data()); }
+    p.inner = 1; p.inner_blocks = 1; p.outer_stride = N; p.n_tiles = rows; p.out_inner = 1; p.out_outer_stride = N;
+    p.out_blk_log2 = -1; p.in_blk_log2 = -1; p.scale = (T)0.5; p.scale_mode = 1;
+    // the buffer: max(staging, exchange) bytes, as TmaRowAliasLayout sizes it
+    const size_t in_bytes = (size_t)G * N * 2 * sizeof(T), x_bytes = (size_t)Cfg::COL_SMEM * G * 2 * sizeof(T);
+    std::vector<T2> buf((in_bytes > x_bytes ? in_bytes : x_bytes) / sizeof(T2) + 1);
+    unsigned char* raw = reinterpret_cast<unsigned char*>(buf.data());
+    auto stage = [&](long long grp) {
+        for (auto& v : buf) { v.x = NAN; v.y = NAN; }
+        long long tiles = rows - grp * G;
+        if (tiles > G) tiles = G;
+        if (tiles <= 0) return;
+        if (SPLIT) {
+            std::memcpy(raw, in_re.data() + grp * G * N, (size_t)tiles * N * sizeof(T));
+            std::memcpy(raw + in_bytes / 2, in_im.data() + grp * G * N, (size_t)tiles * N * sizeof(T));
+        } else {
+            std::memcpy(raw, in_c.data() + grp * G * N, (size_t)tiles * N * sizeof(T2));
+        }
+    };
+    const long long n_groups = (rows + G - 1) / G;
+    stage(0);
+    for (long long grp = 0; grp < n_groups; ++grp) {
+        std::vector<TileThread<Cfg, SPLIT, INV>> th(Cfg::THREADS);
+        for (int tid = 0; tid < Cfg::THREADS; ++tid) {
+            th[tid].setup(tid, grp, p);
+            th[tid].load_smem(raw, raw + in_bytes / 2);
+        }
+        emu_stages_hook<Cfg, SPLIT, INV, 0>(th, p, buf.data(), buf.size(), [&] { stage(grp + 1); });
+        for (auto& t : th) t.store(p);
+    }
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long r = 0; r < rows; ++r) {
+        for (int n = 0; n < N; ++n) line[n] = INV ? cld(in_im[r * N + n], in_re[r * N + n]) : cld(in_re[r * N + n], in_im[r * N + n]);
+        ref_fft(line);
+        for (int n = 0; n < N; ++n) {
+            cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+            want *= 0.5L;
+            cld got = SPLIT ? cld(out_re[r * N + n], out_im[r * N + n]) : cld(out_c[r * N + n].x, out_c[r * N + n].y);
+            double e = (double)std::abs(got - want);
+            if (!(e == e)) e = 1e30;
+            max_err = std::max(max_err, e);
+            max_mag = std::max(max_mag, (double)std::abs(want));
+        }
+    }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <class Cfg>
+static void check_alias_row(const char* name) {
+    using T = typename Cfg::T;
+    const double tol = sizeof(T) == 4 ? 3e-6 : 1e-14;
+    double e0 = run_alias_row<Cfg, false, false>(2 * Cfg::G + 1, 71), e1 = run_alias_row<Cfg, false, true>(Cfg::G + 1, 72),
+           e2 = run_alias_row<Cfg, true, false>(2 * Cfg::G + 1, 73);
+    bool ok = e0 < tol && e1 < tol && e2 < tol;
+    std::printf("%-44s rows, staging slot = exchange buffer  err fwd=%.2e inv=%.2e split=%.2e %s\n", name, e0, e1, e2, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 // One pass of the thread program over the arrays `p` points at (plain or four-step "A" mode).
 template <class Cfg, bool SPLIT, bool INV, bool FS>
 static void emu_pass(const PassParams<typename Cfg::T>& p) {

@@ -183,3 +183,53 @@ def test_slab_exchange_layout_world2(shape):
         assert p.exitcode == 0
     for rank, e1, e2, e3, e4 in res:
         assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12 and e4 < 1e-12, (rank, e1, e2, e3, e4)
+
+
+def _schedule(built_lib, ranks, C, K, hidden, cols=0):
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 14)
+    assert built_lib.b2fft_slab_schedule_preview(ranks, C, K, int(hidden), cols, buf, len(buf)) == 0
+    cells = []
+    for item in buf.value.decode().strip(";").split(";"):
+        k, c = item.split(":")
+        ks = list(range(K)) if k == "all" else [int(k)]
+        cs = list(range(int(c.split("-")[0]), int(c.split("-")[1]) + 1)) if "-" in c else [int(c)]
+        cells.append((k == "all", ks, cs))
+    return cells
+
+
+@pytest.mark.parametrize("ranks,C,K,hidden,cols", [(8, 8, 8, 1, 0), (4, 8, 8, 1, 0), (8, 16, 4, 1, 0), (8, 8, 4, 1, 8), (2, 8, 1, 0, 0),
+                                                  (8, 8, 4, 0, 0), (16, 8, 8, 1, 0), (8, 8, 8, 1, 1)])
+def test_slab_launch_order(built_lib, ranks, C, K, hidden, cols):
+    """csrc/slab.cu's order of the X-pass launches (b2fft_slab_schedule_preview, no device): every (z-chunk, y-chunk) cell is
+    sent exactly once; a launch never needs a z-chunk later than the ones the exchange stream has already waited for plus the
+    next one (the Y launch completes its chunks in order); with the hidden Y pass the columns that leave z-chunk by z-chunk
+    come first and ALL of them complete before the first whole-column launch, whose columns then complete one at a time (so
+    their Z passes spread out); the default number of early columns follows the rank count (3 of 8 on 8 ranks, 4 of 8 on 4)."""
+    cells = _schedule(built_lib, ranks, C, K, hidden, cols)
+    seen = {}
+    waited = -1                      # highest z-chunk whose Y pass the exchange stream has waited for
+    completed = []                   # columns in the order they complete
+    for whole, ks, cs in cells:
+        need = max(ks)
+        assert need <= waited + K if whole else need <= waited + 1
+        waited = max(waited, need)
+        for k in ks:
+            for c in cs:
+                assert (k, c) not in seen
+                seen[(k, c)] = True
+        for c in cs:
+            if all((k, c) in seen for k in range(K)) and c not in completed:
+                completed.append(c)
+    assert len(seen) == K * C and sorted(completed) == list(range(C))
+    if hidden:
+        early = cells[0][2]
+        want = cols if cols else max(1, min(C, int(C * 0.364 * ranks / (ranks - 1) + 0.5)))      # 8 ranks: 3 of 8; 4 ranks: 4 of 8
+        assert cols or C != 8 or want == {8: 3, 4: 4, 16: 3}[ranks]
+        assert len(early) == min(want, C) and early == list(range(len(early)))
+        assert [c[1] for c in cells[:K]] == [[k] for k in range(K)] and all(c[2] == early for c in cells[:K])
+        late = cells[K:]
+        assert all(whole for whole, _, _ in late) and [cs for _, _, cs in late] == [[c] for c in range(len(early), C)]
+        assert completed == list(range(C))
+    else:
+        assert all(not whole and len(cs) == 1 for whole, _, cs in cells) and len(cells) == K * C
