@@ -32,6 +32,13 @@ CASES = [
     # axes longer than one CTA holds: the four-step path here, the reference's global-kernel chains there
     ("n32768_fwd", (32768,), 1, np.complex64, False, True, 1.0),
     ("d2_4096x8_inv", (4096, 8), 1, np.complex64, True, True, 1.0),
+    # round 2 kernels: short rows (16-byte loads + warp shuffles), long rows (staging slot = exchange buffer), a 2048-long
+    # strided axis (streamed fused two-step kernel)
+    ("n16_b64_split_fwd", (16,), 64, np.float32, False, True, 1.0),
+    ("n32_b8_inv", (32,), 8, np.complex64, True, True, 1.0),
+    ("n16384_fwd", (16384,), 1, np.complex64, False, True, 1.0),
+    ("n8192_dp_inv", (8192,), 1, np.complex128, True, True, 1.0),
+    ("d2_2048x16_fwd", (2048, 16), 1, np.complex64, False, True, 1.0),
 ]
 
 
