@@ -245,6 +245,7 @@ struct PassParams {
     int fs_bulk;              // four-step pass A, inner0 == 1: whole output rows leave as cp.async.bulk (kernels.cuh)
     int tma_store;            // strided persistent kernels: output tiles leave as TMA tensor stores (kernels.cuh)
     int blk_bulk;             // blocked stores of a contiguous-axis pass go out as TMA bulk copies (kernels.cuh)
+    int split_bulk;           // split-layout rows of the TMA-staged row kernel: output planes leave as TMA bulk copies
     int max_ctas;             // > 0: cap on the grid of the plain kernels (CTAs then stride over the tiles)
     // four-step "A" pass (FS kernels only): the transformed axis of length N = N1*N2 is split as
     // n = n1*N2 + n2; this pass transforms over n1 (length Cfg::N = N1, element stride N2*inner0,

@@ -85,6 +85,48 @@ __device__ __forceinline__ void store_blocked_bulk(TileThread<Cfg, false, INV, f
     if (!own) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused (after a barrier)
 }
 
+// Split-layout rows: the two output planes of the finished lines are laid out densely in the (now idle) exchange buffer and
+// every plane of the group leaves as ONE cp.async.bulk -- instead of 4-byte global stores, of which the split layout needs
+// twice as many instructions as the interleaved one needs 8-byte ones (the L1/LSU data pipe is the co-limiter of the row
+// kernels).
+template <class Cfg, class TH>
+__device__ __forceinline__ void store_split_bulk(TH& th, const PassParams<typename Cfg::T>& p, typename Cfg::T* smem, long long grp) {
+    using T = typename Cfg::T;
+    constexpr int N = Cfg::N, TPC = Cfg::TPC, S = Cfg::S, G = Cfg::G;
+    constexpr int R = Cfg::R(S - 1), LG = ilog2(R), BPT = Cfg::BPT(S - 1);
+    __syncthreads();                                   // the last exchange has been read by everyone
+    th.apply_scale(p);
+    if (th.active) {
+        T* dre = smem + (long long)th.g * N + th.t;
+        T* dim = dre + (long long)G * N;
+        static_for<0, BPT>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            static_for<0, R>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                T xr, xi;
+                csplit(th.v[i * R + brev(k, LG)], xr, xi);
+                dre[(i + k * BPT) * TPC] = xr;
+                dim[(i + k * BPT) * TPC] = xi;
+            });
+        });
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy reads
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        long long tiles = p.n_tiles - grp * G;
+        if (tiles > G) tiles = G;
+        const unsigned bytes = (unsigned)(tiles * N * sizeof(T));
+        T* gdst = (threadIdx.x == 0 ? p.out0 : p.out1) + grp * G * (long long)N;
+        const T* ssrc = smem + (long long)threadIdx.x * G * N;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                     "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the buffer may be reused (after the next barrier)
+    }
+    __syncthreads();
+}
+
 // Four-step pass A on a contiguous axis (inner0 == 1): column w of the tile becomes the N1 contiguous
 // outputs [n2][k1 = 0..N1).  The tile is staged TRANSPOSED in shared memory (row pitch N1 + 16 bytes:
 // conflict-free for the column-major writes, 16-byte aligned for the copy) and every row leaves as ONE
@@ -268,8 +310,12 @@ tile_fft_kernel_tma_row(const __grid_constant__ PassParams<typename Cfg::T> p) {
             issue(grp + (long long)NBUF * stride, slot);
         }
         run_stages<Cfg, SPLIT, INV, 0>(th, p, xbuf);
+        if constexpr (SPLIT && Cfg::S > 1) {
+            if (p.split_bulk) { store_split_bulk<Cfg>(th, p, reinterpret_cast<T*>(xbuf), grp); continue; }
+        }
         th.store(p);
     }
+    if constexpr (SPLIT && Cfg::S > 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ persistent TMA-fed kernel for LONG rows: staging slot = exchange buffer
@@ -1230,7 +1276,15 @@ struct VariantOpsTma {
         if (ctas > slots()) ctas = slots();
         const dim3 grid((unsigned)ctas), block(Cfg::THREADS);
         const size_t sm = L::TOTAL;
-        if (split) tile_fft_kernel_tma_row<Cfg, true, false, MINB, NBUF><<<grid, block, sm, stream>>>(p);
+        if (split) {
+            // whole output planes of a group leave as bulk copies when the plain dense layout and the 16-byte rules allow it
+            static const bool sb_ok = [] { const char* e = getenv("B2FFT_SPLIT_BULK"); return !e || atoi(e) != 0; }();
+            PassParams<T> q = p;
+            q.split_bulk = sb_ok && Cfg::S > 1 && p.out_blk_log2 < 0 && p.outer_div <= 0 && p.fs_t1 == nullptr && p.out_inner == 1 &&
+                           p.out_outer_stride == Cfg::N && ((uintptr_t)p.out0 % 16) == 0 && ((uintptr_t)p.out1 % 16) == 0 &&
+                           ((size_t)Cfg::N * sizeof(T)) % 16 == 0;
+            tile_fft_kernel_tma_row<Cfg, true, false, MINB, NBUF><<<grid, block, sm, stream>>>(q);
+        }
         else if (inv) tile_fft_kernel_tma_row<Cfg, false, true, MINB, NBUF><<<grid, block, sm, stream>>>(p);
         else tile_fft_kernel_tma_row<Cfg, false, false, MINB, NBUF><<<grid, block, sm, stream>>>(p);
         return cudaGetLastError();
