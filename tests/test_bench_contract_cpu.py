@@ -26,6 +26,9 @@ def test_reference_arm_json_contract():
     assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("C2C FFT GFLOP/s") and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"].startswith("cfg1")
+    sys.path.insert(0, ROOT)
+    import bench                                       # both arms print workload_config(): the driver's same-config check
+    assert d["config"] == bench.workload_config("cfg1", bench.WORKLOADS["cfg1"][1])
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["sample"]
     try:

@@ -125,6 +125,30 @@ def test_xslab_plan_hidden_y_pass_single_rank(cuda_device, chunks, columns):
     ref.close()
 
 
+@pytest.mark.parametrize("shape,wave", [((64, 128, 32), (5, 17, 3)), ((16, 2048, 64), (15, 1029, 63)), ((8, 16, 2048), (1, 0, 2047))])
+def test_xslab_plane_wave_closed_form(cuda_device, shape, wave):
+    """Closed form used to verify transforms too large for a float64 oracle: a plane wave
+    exp(2 pi i (kz z/Z + ky y/Y + kx x/X)) transforms to N at (kz, ky, kx) and zero elsewhere."""
+    import torch
+    from pyfft_b200.dist import SlabPlan
+    Z, Y, X = shape
+    kz, ky, kx = wave
+    plan = SlabPlan(shape, dtype=np.complex64, exchange="xslab", chunks=4, z_chunks=2, normalize=False)
+    z = torch.arange(Z, device=cuda_device, dtype=torch.float64).view(Z, 1, 1) * (kz / Z)
+    y = torch.arange(Y, device=cuda_device, dtype=torch.float64).view(1, Y, 1) * (ky / Y)
+    x = torch.arange(X, device=cuda_device, dtype=torch.float64).view(1, 1, X) * (kx / X)
+    ph = 2.0 * np.pi * ((z + y + x) % 1.0)
+    plan.slab.copy_(torch.complex(torch.cos(ph), torch.sin(ph)).to(torch.complex64))
+    out = plan.forward()                                    # [Y][Z][X] on one rank
+    torch.cuda.synchronize()
+    n = float(Z * Y * X)
+    want = torch.zeros_like(out)
+    want[ky, kz, kx] = n
+    err = float((out - want).abs().max().item()) / n
+    assert err < 1e-5 * np.log2(n), err
+    plan.close()
+
+
 def test_batch_sharded_plan_single_rank(cuda_device):
     import torch
     from pyfft_b200.dist import BatchShardedPlan
