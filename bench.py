@@ -451,6 +451,45 @@ def slab_record(args, world, rank, dev):
         rec["parity"] = {"error": str(exc)[:300]}
     torch.cuda.empty_cache()
 
+    # ---- parity of the pipeline the 2048^3 timing below runs from 4 ranks on (Y pass as ONE persistent launch with progress
+    #      counters, hidden under the exchange): the 512^3 case above cannot take it (its Y axis is 512 long), so a
+    #      [8G][2048][16G] array goes through the same default SlabPlan and is gathered on rank 0 against numpy.fft.fftn
+    if world > 1:
+        try:
+            shp = (8 * world, 2048, 16 * world)
+            plan = SlabPlan(shp, dtype=np.complex64, exchange="xslab", chunks=args.slab_chunks)
+            hidden = "hidden under the exchange" in plan.describe()
+            gen.manual_seed(5500 + rank)
+            plan.slab.copy_(torch.view_as_complex(torch.randn(plan.L["Zl"], shp[1], shp[2], 2, device=dev, generator=gen)))
+            x_local = plan.slab.clone()
+            plan.forward()
+            torch.cuda.synchronize(dev)
+            xr, yr = torch.view_as_real(x_local).contiguous(), torch.view_as_real(plan.xslab).contiguous()
+            px = [torch.empty_like(xr) for _ in range(world)] if rank == 0 else None
+            py = [torch.empty_like(yr) for _ in range(world)] if rank == 0 else None
+            dist.gather(xr, px, dst=0)
+            dist.gather(yr, py, dst=0)
+            plan.inverse()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([float(((plan.slab - x_local).abs() ** 2).sum().double().item()),
+                              float((x_local.abs() ** 2).sum().double().item()), float(plan.status())], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            num, den, bad = t.tolist()
+            ph = {"shape": list(shp), "hidden_y_pass": bool(hidden), "roundtrip_rel_l2": math.sqrt(num / den), "flag_timeouts": int(bad),
+                  "tolerance": 1e-5 * math.log2(float(shp[0]) * shp[1] * shp[2])}
+            if rank == 0:
+                full = torch.cat([torch.view_as_complex(q) for q in px], dim=0).cpu().numpy()
+                got = torch.cat([torch.view_as_complex(q).permute(1, 0, 2) for q in py], dim=2).cpu().numpy()
+                want = np.fft.fftn(full.astype(np.complex128))
+                ph["fwd_rel_l2"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+                del full, got, want
+            rec["parity_hidden_y"] = ph
+            plan.close()
+            del plan, x_local, px, py
+        except Exception as exc:
+            rec["parity_hidden_y"] = {"error": str(exc)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- timing at 2048^3
     n = args.slab_size
     size = float(n) ** 3
