@@ -459,7 +459,8 @@ int launch_pass(b2fft_plan* pl, const Pass& ps, const void* in0, const void* in1
     if (registry().v[vi].kind != 0) {   // TMA needs 16-byte aligned sources (and 16-byte multiples as row pitch)
         const size_t pitch = (size_t)ps.inner * (split ? sizeof(T) : 2 * sizeof(T));
         if (((uintptr_t)in0 % 16) != 0 || (split && ((uintptr_t)in1 % 16) != 0) ||
-            (registry().v[vi].kind == 2 && (pitch % 16 != 0 || outer_count > 0x7fffffffLL)))
+            (registry().v[vi].kind == 2 && (pitch % 16 != 0 || outer_count > 0x7fffffffLL)) ||
+            (registry().v[vi].kind == 4 && (((uintptr_t)out0 % 16) != 0 || (split && ((uintptr_t)out1 % 16) != 0))))   // 16-byte stores too
             vi = ps.fallback;
     }
     const bool in_blocked = pl->in_nblocks > 0 && &ps == &pl->passes.front();

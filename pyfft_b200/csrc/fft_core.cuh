@@ -902,6 +902,85 @@ struct ShflRow {
     }
 };
 
+// ---- the same with FOUR elements per lane and 16-byte stores as well: N/4 lanes share a row, lane l holds positions
+// p = 2l + b + (N/2) h (b, h in {0, 1}): two 16-byte loads, one from each half of the row, both fully coalesced.  Stage 0
+// (half = N/2) pairs the lane's own h = 0 / 1 registers (lane-dependent twiddle w_N^(2l+b)); the stages with half = N/4 .. 2
+// pair lane l with lane l ^ (half/2) through shfl.sync.bfly (all four registers); the last stage (half = 1) pairs b = 0 / 1.
+// Position p holds X[brev(p)] = X[h + 2 brev_{L-2}(l) + (N/2) b]: the lane's h = 0 / 1 outputs are ADJACENT, so the results
+// leave as two 16-byte stores {X[2r], X[2r+1]} and {X[2r + N/2], X[2r+1 + N/2]}, r = brev_{L-2}(l) -- per instruction the
+// lanes of a row cover one contiguous half row, like the loads.  One shuffle stage fewer than ShflRow for the same N.
+template <int LOG2N, bool INV>
+struct ShflRow4 {
+    using T = float;
+    using C = cpx<T>;
+    static_assert(LOG2N >= 2 && LOG2N <= 7, "N/4 lanes of one warp share a row");
+    static constexpr int N = 1 << LOG2N, LP = N / 4, NSX = LOG2N - 2;     // lanes per row, cross-lane stages
+    C tw0[2];                         // stage 0: w_N^(2l + b)
+    C tw[NSX > 0 ? NSX : 1][2];       // cross-lane stage s = 1 .. NSX: upper-output twiddle for b = 0, 1 (the same for h = 0, 1)
+    bool upper[NSX > 0 ? NSX : 1];
+    B2_HD static C root(int q, int len) {                      // exp(-2 pi i q / len)
+        T sn, cs;
+#if defined(__CUDA_ARCH__)
+        sincospif((T)(2 * q) / (T)len, &sn, &cs);
+#else
+        sn = (T)std::sin(2.0 * 3.14159265358979323846 * q / len);
+        cs = (T)std::cos(2.0 * 3.14159265358979323846 * q / len);
+#endif
+        return cmake<T>(cs, -sn);
+    }
+    B2_HD void init(int l) {
+        for (int b = 0; b < 2; ++b) tw0[b] = root(2 * l + b, N);
+        static_for<0, NSX>([&](auto sc) {
+            constexpr int s = decltype(sc)::value + 1;         // stage index, half = N >> (s+1) in [2, N/4]
+            constexpr int half = N >> (s + 1);
+            upper[s - 1] = (l & (half >> 1)) != 0;
+            for (int b = 0; b < 2; ++b) tw[s - 1][b] = root(2 * (l % (half / 2)) + b, 2 * half);
+        });
+    }
+    B2_HD static C sel(bool c, const C& a, const C& b) {
+#if defined(__CUDA_ARCH__)
+        C r; r.v = c ? a.v : b.v; return r;
+#else
+        return c ? a : b;
+#endif
+    }
+    // registers: v[2h + b]
+    B2_HD void first(C (&v)[4]) const {
+        for (int b = 0; b < 2; ++b) {
+            const C lo = v[b], hi = v[2 + b];
+            v[b] = cadd(lo, hi);
+            v[2 + b] = cmul<INV>(csub(lo, hi), tw0[b]);
+        }
+    }
+    template <int sx>                 // cross-lane stage sx = 0 .. NSX-1; o = the partner lane's four registers
+    B2_HD void stage(C (&v)[4], const C (&o)[4]) const {
+        for (int r = 0; r < 4; ++r) {
+            const C up = cmul<INV>(csub(o[r], v[r]), tw[sx][r & 1]);
+            const C lo = cadd(v[r], o[r]);
+            v[r] = sel(upper[sx], up, lo);
+        }
+    }
+    B2_HD static void last(C (&v)[4]) {
+        for (int h = 0; h < 2; ++h) {
+            const C a = v[2 * h], b = v[2 * h + 1];
+            v[2 * h] = cadd(a, b);
+            v[2 * h + 1] = csub(a, b);
+        }
+    }
+    // v[2h + b] holds X[h + 2 r + (N/2) b], r = out_index(l)
+    B2_HD static int out_index(int l) {
+        int r = 0;
+        for (int i = 0; i < NSX; ++i) r |= ((l >> i) & 1) << (NSX - 1 - i);
+        return r;
+    }
+    B2_HD static void scale(C (&v)[4], T sc, int mode) {
+        if (mode == 1) { for (int r = 0; r < 4; ++r) v[r] = cscale(v[r], sc); }
+        else if (mode == 2) {
+            for (int r = 0; r < 4; ++r) { T xr, xi; csplit(v[r], xr, xi); v[r] = cmake<T>(xr / sc, xi / sc); }
+        }
+    }
+};
+
 // ------------------------------------------------------------------ lane-pair FFT (warp-shuffle exchange)
 // A length-N = 2E transform shared by two lanes of a warp (t = 0, 1): lane t holds x[2j + t] in v[j], does the E-point
 // FFT of its residue class in registers, lane 1 applies w_N^ka, and the final radix-2 stage pairs Z_0[ka] with Z_1[ka]:

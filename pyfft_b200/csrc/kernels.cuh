@@ -1120,6 +1120,79 @@ row_shfl_kernel(const __grid_constant__ PassParams<float> p) {
     }
 }
 
+// ... four elements per lane (ShflRow4): 16-byte loads AND 16-byte stores, one shuffle stage fewer.  N = 4 .. 128.
+template <int LOG2N, bool SPLIT, bool INV>
+__global__ void __launch_bounds__(256)
+row_shfl4_kernel(const __grid_constant__ PassParams<float> p) {
+    using R = ShflRow4<LOG2N, INV>;
+    using C = cpx<float>;
+    constexpr int N = R::N, LP = R::LP, RPW = 32 / LP;                  // rows per warp and step
+    constexpr int U = 2;                                                // independent rows per thread in flight
+    const int lane = (int)threadIdx.x & 31, l = lane % LP;
+    R r;
+    r.init(l);
+    const int k0 = 2 * R::out_index(l);
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (long long row0 = warp * (RPW * U); row0 < p.n_tiles; row0 += warps * (RPW * U)) {   // warp-uniform: the shuffles need every lane
+        C v[U][4];
+        static_for<0, U>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const long long row = row0 + u * RPW + lane / LP;
+            static_for<0, 4>([&](auto rc) { v[u][decltype(rc)::value] = cmake<float>(0.f, 0.f); });
+            if (row < p.n_tiles) {
+                static_for<0, 2>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    if constexpr (SPLIT) {
+                        float2 re, im;
+                        const float2* pr = reinterpret_cast<const float2*>(p.in0 + row * p.outer_stride + (N / 2) * h) + l;
+                        const float2* pi = reinterpret_cast<const float2*>(p.in1 + row * p.outer_stride + (N / 2) * h) + l;
+                        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(re.x), "=f"(re.y) : "l"(pr));
+                        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(im.x), "=f"(im.y) : "l"(pi));
+                        v[u][2 * h] = cmake<float>(re.x, im.x); v[u][2 * h + 1] = cmake<float>(re.y, im.y);
+                    } else {
+                        float4 q;
+                        const float4* ps = reinterpret_cast<const float4*>(reinterpret_cast<const vec2<float>*>(p.in0) + row * p.outer_stride + (N / 2) * h) + l;
+                        asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(ps));
+                        v[u][2 * h] = cmake<float>(q.x, q.y); v[u][2 * h + 1] = cmake<float>(q.z, q.w);
+                    }
+                });
+            }
+        });
+        static_for<0, U>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const long long row = row0 + u * RPW + lane / LP;
+            r.first(v[u]);
+            static_for<0, R::NSX>([&](auto sc) {
+                constexpr int sx = decltype(sc)::value;
+                constexpr int mask = (N >> (sx + 2)) >> 1;
+                C o[4];
+                static_for<0, 4>([&](auto rc) { o[decltype(rc)::value] = b2_shfl_xor_c(v[u][decltype(rc)::value], mask); });
+                r.template stage<sx>(v[u], o);
+            });
+            R::last(v[u]);
+            R::scale(v[u], p.scale, p.scale_mode);
+            if (row < p.n_tiles) {
+                static_for<0, 2>([&](auto bc) {
+                    constexpr int b = decltype(bc)::value;                  // {X[k0 + (N/2) b], X[k0 + 1 + (N/2) b]} = registers b, 2 + b
+                    float ar, ai, br, bi;
+                    csplit(v[u][b], ar, ai);
+                    csplit(v[u][2 + b], br, bi);
+                    if constexpr (SPLIT) {
+                        float2* orow = reinterpret_cast<float2*>(p.out0 + row * p.out_outer_stride + (N / 2) * b + k0);
+                        float2* irow = reinterpret_cast<float2*>(p.out1 + row * p.out_outer_stride + (N / 2) * b + k0);
+                        *orow = make_float2(ar, br);
+                        *irow = make_float2(ai, bi);
+                    } else {
+                        float4* orow = reinterpret_cast<float4*>(reinterpret_cast<vec2<float>*>(p.out0) + row * p.out_outer_stride + (N / 2) * b + k0);
+                        *orow = make_float4(ar, ai, br, bi);
+                    }
+                });
+            }
+        });
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct KernelVariant {
     const char* name;
@@ -1888,6 +1961,48 @@ struct VariantOpsShfl {
         return v;
     }
 };
+
+template <int LOG2N>
+struct VariantOpsShfl4 {
+    static int& sms() { static int s[B2_MAX_DEVICES] = {}; return s[b2_current_device()]; }
+    static cudaError_t prepare() { return VariantOpsShfl<2>::prepare(); }
+    static cudaError_t launch(int split, int inv, const void* params, cudaStream_t stream) {
+        const PassParams<float>& p = *static_cast<const PassParams<float>*>(params);
+        if (p.out_blk_log2 >= 0 || p.outer_div > 0 || p.fs_t1 != nullptr || p.inner != 1 || p.progress != nullptr ||
+            (p.in_blk_log2 >= 0 && p.in_blk[0] != nullptr))
+            return cudaErrorNotSupported;
+        // 16-byte vectors on both sides: the output planes / array must be 16-byte aligned as well (the planner's alignment rule
+        // covers the input only)
+        if (((uintptr_t)p.out0 % 16) != 0 || (split && ((uintptr_t)p.out1 % 16) != 0)) return cudaErrorNotSupported;
+        if (p.n_tiles <= 0) return cudaSuccess;
+        if (VariantOpsShfl<2>::sms() <= 0) { cudaError_t e = prepare(); if (e != cudaSuccess) return e; }
+        constexpr int LP = (1 << LOG2N) / 4;
+        long long ctas = (p.n_tiles * LP + 2 * 256 - 1) / (2 * 256);      // two rows per thread and step
+        const long long cap = (long long)VariantOpsShfl<2>::sms() * 32;
+        if (ctas > cap) ctas = cap;
+        const dim3 grid((unsigned)ctas), block(256);
+        if (split) row_shfl4_kernel<LOG2N, true, false><<<grid, block, 0, stream>>>(p);
+        else if (inv) row_shfl4_kernel<LOG2N, false, true><<<grid, block, 0, stream>>>(p);
+        else row_shfl4_kernel<LOG2N, false, false><<<grid, block, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    static int occupancy() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, row_shfl4_kernel<LOG2N, false, false>, 256, 0) != cudaSuccess) return -1;
+        return n;
+    }
+    static KernelVariant make(const char* name) {
+        KernelVariant v = VariantOpsShfl<LOG2N < 6 ? LOG2N : 6>::make(name);
+        v.log2n = LOG2N;
+        v.G = 1024 / (1 << LOG2N); v.E = 4;
+        v.radix[0] = 1 << LOG2N;
+        v.launch = &launch;
+        v.prepare = &prepare;
+        v.occupancy = &occupancy;
+        return v;
+    }
+};
+#define B2_VR4(L) out.push_back(::b2::VariantOpsShfl4<L>::make("float_n" #L "_w1_shfl4"));
 
 // B2_VR(log2n): short-row kernel, complex64 / split float32, 16-byte accesses + warp-shuffle exchanges
 #define B2_VR(L) out.push_back(::b2::VariantOpsShfl<L>::make("float_n" #L "_w1_shfl"));

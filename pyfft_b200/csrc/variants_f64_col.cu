@@ -19,6 +19,7 @@ void register_f64_col(std::vector<KernelVariant>& out) {
 #define XW B2_VW
 #define XP B2_VP
 #define XR B2_VR
+#define XR4 B2_VR4
 #define XTA B2_VTA
 #include "variants.def"
 #undef X
@@ -36,6 +37,7 @@ void register_f64_col(std::vector<KernelVariant>& out) {
 #undef XW
 #undef XP
 #undef XR
+#undef XR4
 #undef XTA
 }
 }  // namespace b2

@@ -942,6 +942,79 @@ static double run_shfl(long long rows, unsigned seed) {
     return max_err / (max_mag > 0 ? max_mag : 1);
 }
 
+// ... and the four-elements-per-lane version (ShflRow4: 16-byte loads AND stores): positions 2l + b + (N/2) h in, X[h + 2r +
+// (N/2) b] out, exactly as row_shfl4_kernel addresses them.
+template <int LOG2N, bool INV>
+static double run_shfl4(long long rows, unsigned seed) {
+    using R = ShflRow4<LOG2N, INV>;
+    using C = cpx<float>;
+    constexpr int N = R::N, LP = R::LP;
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    std::vector<float> re(rows * N), im(rows * N), ore(rows * N, NAN), oim(rows * N, NAN);
+    for (auto& v : re) v = (float)nd(rng);
+    for (auto& v : im) v = (float)nd(rng);
+    for (long long row = 0; row < rows; ++row) {
+        std::vector<R> th(LP);
+        std::vector<std::array<C, 4>> v(LP), o(LP);
+        for (int l = 0; l < LP; ++l) {
+            th[l].init(l);
+            for (int h = 0; h < 2; ++h)
+                for (int b = 0; b < 2; ++b) {
+                    const long long p = row * N + 2 * l + b + (N / 2) * h;
+                    v[l][2 * h + b] = cmake<float>(re[p], im[p]);
+                }
+            C a[4] = {v[l][0], v[l][1], v[l][2], v[l][3]};
+            th[l].first(a);
+            v[l] = {a[0], a[1], a[2], a[3]};
+        }
+        static_for<0, R::NSX>([&](auto sc) {
+            constexpr int sx = decltype(sc)::value;
+            constexpr int mask = (N >> (sx + 2)) >> 1;
+            for (int l = 0; l < LP; ++l) o[l] = v[l ^ mask];
+            for (int l = 0; l < LP; ++l) {
+                C a[4] = {v[l][0], v[l][1], v[l][2], v[l][3]}, b[4] = {o[l][0], o[l][1], o[l][2], o[l][3]};
+                th[l].template stage<sx>(a, b);
+                v[l] = {a[0], a[1], a[2], a[3]};
+            }
+        });
+        for (int l = 0; l < LP; ++l) {
+            C a[4] = {v[l][0], v[l][1], v[l][2], v[l][3]};
+            R::last(a);
+            R::scale(a, 0.5f, 1);
+            const int r = R::out_index(l);
+            for (int h = 0; h < 2; ++h)
+                for (int b = 0; b < 2; ++b) {
+                    const long long k = row * N + h + 2 * r + (N / 2) * b;
+                    ore[k] = a[2 * h + b].x; oim[k] = a[2 * h + b].y;
+                }
+        }
+    }
+    double max_err = 0, max_mag = 0;
+    std::vector<cld> line(N);
+    for (long long row = 0; row < rows; ++row) {
+        for (int n = 0; n < N; ++n) line[n] = INV ? cld(im[row * N + n], re[row * N + n]) : cld(re[row * N + n], im[row * N + n]);
+        ref_fft(line);
+        for (int n = 0; n < N; ++n) {
+            cld want = INV ? cld(line[n].imag(), line[n].real()) : line[n];
+            want *= 0.5L;
+            double e = (double)std::abs(cld(ore[row * N + n], oim[row * N + n]) - want);
+            if (!(e == e)) e = 1e30;
+            max_err = std::max(max_err, e);
+            max_mag = std::max(max_mag, (double)std::abs(want));
+        }
+    }
+    return max_err / (max_mag > 0 ? max_mag : 1);
+}
+
+template <int LOG2N>
+static void check_shfl4(const char* name) {
+    double e0 = run_shfl4<LOG2N, false>(5, 81), e1 = run_shfl4<LOG2N, true>(3, 82);
+    bool ok = e0 < 2e-6 && e1 < 2e-6;
+    std::printf("%-44s short rows (4 per lane, lane shuffles) N=%d  err fwd=%.2e inv=%.2e %s\n", name, 1 << LOG2N, e0, e1, ok ? "ok" : "FAIL");
+    if (!ok) ++g_fail;
+}
+
 template <int LOG2N>
 static void check_shfl(const char* name) {
     double e0 = run_shfl<LOG2N, false, false>(5, 61), e1 = run_shfl<LOG2N, true, false>(3, 62);
