@@ -81,12 +81,14 @@ def test_layout_and_pitch_aware_variant_choice(built_lib):
 
 def test_short_rows_take_the_shuffle_kernel(built_lib):
     # complex64 / split float32 rows of 4 .. 32 elements: 16-byte accesses + warp-shuffle exchanges (row_shfl_kernel) ...
-    for n in (4, 8, 16, 32):
+    for n in (4, 8, 16):
         assert _preview(built_lib, n)[0]["variant"] == "float_n%d_w1_shfl" % (n.bit_length() - 1)
         assert _preview(built_lib, n, layout=1)[0]["variant"].endswith("_shfl")
+    for n in (32, 64):           # four elements per lane: 16-byte stores as well, one shuffle stage fewer
+        assert _preview(built_lib, n)[0]["variant"] == "float_n%d_w1_shfl4" % (n.bit_length() - 1)
     assert _preview(built_lib, 16, 16, 16)[0]["variant"].endswith("_shfl")        # the X pass of a small 3-D transform
-    # ... not for N = 2 and N >= 64 (the tile program is at the copy bandwidth there), not for double precision
-    assert "_shfl" not in _preview(built_lib, 2)[0]["variant"] and "_shfl" not in _preview(built_lib, 64)[0]["variant"]
+    # ... not for N = 2 and N >= 128 (the tile program is at the copy bandwidth there), not for double precision
+    assert "_shfl" not in _preview(built_lib, 2)[0]["variant"] and "_shfl" not in _preview(built_lib, 128)[0]["variant"]
     assert "_shfl" not in _preview(built_lib, 16, prec=1)[0]["variant"]
 
 
